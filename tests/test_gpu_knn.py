@@ -1,0 +1,116 @@
+"""GPU parity: radius-bounded 1-NN (vb200_knn1) against the oracle — indices AND double distances must be
+bit-identical (integer/index work).  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from conftest import small_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scene():
+    return small_scene(n_scene=120000, n_objects=3, m=3000)
+
+
+def test_knn_matches_oracle_bitexact(vb, oracle, scene):
+    tgt = scene["scene_xyz"]
+    q = np.concatenate([
+        vb.synth.knn_queries(tgt, 20000, sigma=0.01),
+        vb.synth.knn_queries(tgt, 5000, sigma=0.08),        # many beyond the radius
+        tgt[:2000],                                          # exactly on scene points: d2 == 0
+        np.random.default_rng(1).uniform(-5, 12, (2000, 3)),  # far outside the room / the grid
+    ])
+    sc = vb.reg.Scene(tgt, 0.075)
+    gi, gd = sc.SearchHybrid1(q, 0.075)
+    oi, od = oracle.Index(tgt, 0.075).knn1(q, 0.075)
+    assert (gi == oi).all()
+    assert (gd == od).all()
+    assert (gi >= 0).sum() > 20000 and (gi < 0).sum() > 2000
+    # a smaller radius on the same grid
+    gi, gd = sc.SearchHybrid1(q, 0.02)
+    oi, od = oracle.Index(tgt, 0.02).knn1(q, 0.02)
+    assert (gi == oi).all() and (gd == od).all()
+
+
+def test_threshold_and_ties(vb, oracle):
+    r = 0.075
+    r2f = float(np.float32(r * r))
+    d_in = np.sqrt(min(r2f, r * r)) * (1 - 1e-9)
+    d_between = np.sqrt((r2f + r * r) / 2)
+    d_out = np.sqrt(max(r2f, r * r)) * (1 + 1e-9)
+    # duplicates and mirrored points give exact ties -> lowest target index wins
+    tgt = np.array([[0, 0, 0.0], [0, 0, 0.0], [1.0, 0, 0], [1.02, 0, 0], [1.0, 0, 0], [5, 5, 5]])
+    q = np.array([[d_in, 0, 0], [d_between, 0, 0], [d_out, 0, 0], [1.01, 0, 0], [1.0, 0, 0], [0, 0, 0.0]])
+    sc = vb.reg.Scene(tgt, r)
+    gi, gd = sc.SearchHybrid1(q, r)
+    oi, od = oracle.Index(tgt, r).knn1(q, r)
+    assert (gi == oi).all() and (gd == od).all()
+    assert gi[0] == 0 and gi[2] == -1 and gi[3] == 2 and gi[4] == 2 and gi[5] == 0
+
+
+def test_near_ties_resolved_in_double(vb, oracle):
+    """Pairs of targets whose distances to the query differ by ~1e-12 relative: float screening cannot
+    separate them, the double re-check must."""
+    rng = np.random.default_rng(2)
+    base = rng.uniform(0, 4, (3000, 3))
+    dirs = rng.normal(size=(3000, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    d = rng.uniform(0.005, 0.05, (3000, 1))
+    a = base + dirs * d
+    b = base - dirs * d * (1 + 1e-12 * rng.choice([-1, 1], (3000, 1)))
+    tgt = np.concatenate([a, b])
+    sc = vb.reg.Scene(tgt, 0.075)
+    gi, gd = sc.SearchHybrid1(base, 0.075)
+    oi, od = oracle.Index(tgt, 0.075).knn1(base, 0.075)
+    assert (gi == oi).all() and (gd == od).all()
+
+
+def test_docs_kat_correspondences(vb, oracle, kat):
+    s, t = kat["src"].astype(np.float64), kat["tgt"].astype(np.float64)
+    T = kat["init"]
+    q = s @ T[:3, :3].T + T[:3, 3]
+    sc = vb.reg.Scene(t, 0.02)
+    gi, gd = sc.SearchHybrid1(q, 0.02)
+    oi, od = oracle.Index(t, 0.02).knn1(q, 0.02)
+    assert (gi == oi).all() and (gd == od).all()
+    # 34 741 correspondences is what the docs publish for this init (icp_registration.rst:56-58); the
+    # transform above is numpy's, so allow the count to move by a couple of threshold cases
+    assert abs(int((gi >= 0).sum()) - 34741) <= 2
+
+
+def test_edge_cases(vb):
+    one = np.array([[1.0, 2.0, 3.0]])
+    sc = vb.reg.Scene(one, 0.1)
+    assert sc.size()["n"] == 1
+    i, d = sc.SearchHybrid1(np.zeros((0, 3)), 0.1)
+    assert len(i) == 0
+    i, d = sc.SearchHybrid1(np.array([[1.0, 2.0, 3.05], [1.0, 2.0, 3.2], [np.nan, 0, 0]]), 0.1)
+    assert list(i) == [0, -1, -1] and d[1] == 0.0
+    with pytest.raises(vb.pkg.VismaB200Error):   # radius beyond the grid's cell
+        sc.SearchHybrid1(one, 0.5)
+    with pytest.raises(vb.pkg.VismaB200Error):
+        sc.SearchHybrid1(one, 0.0)
+
+
+def test_full_size_properties(vb):
+    """BASELINE size (2 M-pt scene): size-independent properties instead of an oracle run."""
+    d = vb.synth.make_room_scene(2_000_000, 8, 100)
+    tgt = d["scene_xyz"]
+    sc = vb.reg.Scene(tgt, 0.075)
+    info = sc.size()
+    assert info["n"] == 2_000_000 and info["fine_cells"] > 0
+    # every scene point finds a neighbour at distance 0 (itself, or a lower-index duplicate)
+    sel = np.random.default_rng(0).choice(len(tgt), 200000, replace=False)
+    i, d2 = sc.SearchHybrid1(tgt[sel], 0.075)
+    assert (d2 == 0).all() and (i <= sel).all() and (tgt[i] == tgt[sel]).all()
+    # reported distance is the distance to the reported point, and no sampled scene point is closer
+    q = vb.synth.knn_queries(tgt, 20000, sigma=0.02)
+    i, d2 = sc.SearchHybrid1(q, 0.075)
+    m = i >= 0
+    dd = q[m] - tgt[i[m]]
+    assert (((dd[:, 0] ** 2 + dd[:, 1] ** 2) + dd[:, 2] ** 2) == d2[m]).all()
+    probe = tgt[np.random.default_rng(1).choice(len(tgt), 2000, replace=False)]
+    dm = ((q[:, None, :] - probe[None, :, :]) ** 2).sum(-1).min(1)
+    r2 = float(np.float32(0.075 * 0.075))
+    assert (np.where(m, d2, r2) <= dm + 1e-15).all()

@@ -1,0 +1,132 @@
+"""The oracle against every golden vector the reference holds for this path:
+the Open3D docs ICP known-answer test and the unit-test golden vectors for 1-NN distances and
+VoxelDownSample.  CPU only."""
+import numpy as np
+
+RAND_REF_NN = [
+    155.013456, 126.672493, 114.606722, 190.747153, 133.079840, 121.137276, 106.805907, 226.190750,
+    131.745147, 172.069584, 247.822223, 119.390962, 21.209580, 68.624498, 136.386737, 149.981320,
+    206.445708, 191.876431, 140.127314, 131.657386, 183.471289, 221.094822, 178.447628, 126.081556,
+    29.338770, 111.453558, 102.236849, 304.969947, 40.823263, 227.787078, 169.129676, 197.146871,
+    167.494524, 174.795150, 142.910946, 263.053174, 122.803815, 238.740548, 116.243401, 180.230879,
+    91.863637, 96.241462, 24.547707, 174.705689, 65.612463, 148.994593, 158.758879, 345.655903,
+    251.182091, 182.235820]  # thirdparty/Open3D/src/UnitTest/Core/Geometry/PointCloud.cpp:1076-1086
+
+VOXEL_REF = np.array([
+    [352.458347, 807.724520, 919.026474], [400.228622, 891.529452, 283.314746],
+    [771.357698, 526.744979, 769.913836], [296.031618, 637.552268, 524.287190],
+    [86.055848, 192.213846, 663.226927], [512.932394, 839.112235, 612.639833],
+    [493.582987, 972.775024, 292.516784], [335.222756, 768.229595, 277.774711],
+    [69.755276, 949.327075, 525.995350], [364.784473, 513.400910, 952.229725],
+    [553.969956, 477.397052, 628.870925], [798.440033, 911.647358, 197.551369],
+    [890.232603, 348.892935, 64.171321], [141.602555, 606.968876, 16.300572],
+    [20.023049, 457.701737, 63.095838], [840.187717, 394.382927, 783.099224],
+    [156.679089, 400.944394, 129.790447], [916.195068, 635.711728, 717.296929],
+    [242.886771, 137.231577, 804.176754], [108.808802, 998.924518, 218.256905]])
+# thirdparty/Open3D/src/UnitTest/Core/Geometry/PointCloud.cpp:679-700
+
+
+def unit_points(unit_rand, n, vmax):
+    r, rmax = unit_rand
+    return (r[:3 * n] * (vmax / rmax)).reshape(n, 3)  # UnitTest::Rand, UnitTest.cpp:75-94
+
+
+def test_nn_distance_golden(oracle, unit_rand):
+    pts = unit_points(unit_rand, 100, 1000.0)
+    idx, d2 = oracle.knn1_brute(pts[50:], pts[:50])  # ComputePointCloudToPointCloudDistance(pc0, pc1)
+    assert np.allclose(np.sqrt(d2), RAND_REF_NN, atol=1e-6)
+    # the grid index returns the same neighbours as the brute-force scan
+    ix = oracle.Index(pts[50:], 400.0)
+    gi, gd = ix.knn1(pts[:50], 400.0)
+    assert (gi == idx).all() and (gd == d2).all()
+
+
+def test_voxel_golden(oracle, unit_rand):
+    pts = unit_points(unit_rand, 20, 1000.0)
+    nrm = unit_points(unit_rand, 20, 10.0)
+    out, out_n = oracle.voxel_downsample(pts, 0.5, nrm)
+    assert len(out) == 20
+    key = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+    assert np.allclose(key(out), key(VOXEL_REF), atol=1e-6)
+    assert np.allclose(np.linalg.norm(out_n, axis=1), 1.0)
+
+
+def test_docs_kat_initial_alignment(oracle, kat):
+    s, t = kat["src"].astype(np.float64), kat["tgt"].astype(np.float64)
+    ix = oracle.Index(t, 0.02)
+    r = ix.registration_icp(s, 0.02, kat["init"], oracle.P2P, max_iter=0)
+    fit, rmse, nc = kat["doc_eval"]
+    assert abs(r["fitness"] - fit) < 5e-7 and abs(r["rmse"] - rmse) < 5e-7 and r["ncorr"] == int(nc)
+    assert r["fitness"] == kat["ref_eval"][0] and r["ncorr"] == int(kat["ref_eval"][2])
+
+
+def test_docs_kat_point_to_point(oracle, kat):
+    s, t = kat["src"].astype(np.float64), kat["tgt"].astype(np.float64)
+    ix = oracle.Index(t, 0.02)
+    r = ix.registration_icp(s, 0.02, kat["init"], oracle.P2P, want_trace=True)
+    fit, rmse, nc = kat["doc_p2p"]
+    assert abs(r["fitness"] - fit) < 5e-7 and abs(r["rmse"] - rmse) < 5e-7 and r["ncorr"] == int(nc)
+    assert np.allclose(r["T"], kat["doc_p2p_T"], atol=5e-9)
+    # and against the compiled reference at full precision, every iteration
+    assert np.allclose(r["T"], kat["ref_p2p_T"], atol=1e-12)
+    tr = kat["ref_trace_p2p"]
+    assert len(r["trace"]) == len(tr)
+    assert (r["trace"][:, 2] == tr[:, 2]).all()
+    assert np.allclose(r["trace"], tr, atol=1e-12)
+
+
+def test_docs_kat_point_to_plane(oracle, kat):
+    s, t, tn = (kat[k].astype(np.float64) for k in ("src", "tgt", "tgt_nrm"))
+    ix = oracle.Index(t, 0.02)
+    r = ix.registration_icp(s, 0.02, kat["init"], oracle.P2PLANE, src_nrm=s, tgt_nrm=tn, want_trace=True)
+    fit, rmse, nc = kat["doc_p2l"]
+    assert abs(r["fitness"] - fit) < 5e-7 and abs(r["rmse"] - rmse) < 5e-7 and r["ncorr"] == int(nc)
+    assert np.allclose(r["T"], kat["doc_p2l_T"], atol=5e-9)
+    assert np.allclose(r["T"], kat["ref_p2l_T"], atol=1e-12)
+    tr = kat["ref_trace_p2l"]
+    assert len(r["trace"]) == len(tr) and (r["trace"][:, 2] == tr[:, 2]).all()
+
+
+def test_reference_error_paths(oracle, kat):
+    s, t = kat["src"][:100].astype(np.float64), kat["tgt"][:1000].astype(np.float64)
+    ix = oracle.Index(t, 0.02)
+    r = ix.registration_icp(s, -1.0, kat["init"], oracle.P2P)  # Registration.cpp:148-151
+    assert r["rc"] == -1 and np.array_equal(r["T"], kat["init"]) and r["fitness"] == 0
+    r = ix.registration_icp(s, 0.02, kat["init"], oracle.P2PLANE)  # :152-157, no normals
+    assert r["rc"] == -1 and np.array_equal(r["T"], kat["init"])
+
+
+def test_solve_and_euler(oracle):
+    rng = np.random.default_rng(0)
+    J = rng.normal(size=(40, 6))
+    A, b = J.T @ J, J.T @ rng.normal(size=40)
+    ok, x = oracle.solve6(A, b)
+    assert ok and np.allclose(A @ x, -b, atol=1e-9)
+    ok, x = oracle.solve6(np.zeros((6, 6)), b)  # det guard -> no solution
+    assert not ok and (x == 0).all()
+    T = oracle.vec6_to_T([0.1, -0.2, 0.3, 1, 2, 3])
+    from visma_b200.synth import rot_xyz
+    assert np.allclose(T[:3, :3], rot_xyz(0.1, -0.2, 0.3)) and np.allclose(T[:3, 3], [1, 2, 3])
+
+
+def test_gravity_estimator_properties(oracle):
+    """4-DoF step (not in the reference): equals the 6-DoF solve when the true motion is yaw+translation,
+    never produces roll/pitch, and its Jacobian matches finite differences."""
+    rng = np.random.default_rng(3)
+    from visma_b200.synth import rot_y, make_T
+    tgt = rng.uniform(-1, 1, (3000, 3))
+    nrm = rng.normal(size=(3000, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    Tt = make_T(rot_y(0.01), [0.004, -0.002, 0.003])
+    src = (tgt - Tt[:3, 3]) @ Tt[:3, :3]  # src = Tt^-1 tgt
+    corr = np.stack([np.arange(3000), np.arange(3000)], 1).astype(np.int32)
+    T4 = oracle.estimate(src, tgt, corr, oracle.P2PLANE_GRAVITY, tgt_nrm=nrm, gravity=(0, 1, 0))
+    T6 = oracle.estimate(src, tgt, corr, oracle.P2PLANE, tgt_nrm=nrm)
+    assert np.allclose(T4, T6, atol=5e-5) and np.allclose(T4, Tt, atol=5e-5)
+    assert abs(T4[1, 1] - 1) < 1e-15 and abs(T4[0, 1]) < 1e-15 and abs(T4[1, 0]) < 1e-15  # no roll/pitch
+    # finite differences of r(theta) = (R(theta) vs - vt).nt at theta=0 vs (vs x nt).g
+    eps = 1e-7
+    vs, vt, nt = src[:50], tgt[:50], nrm[:50]
+    r = lambda th: np.einsum("ij,ij->i", vs @ rot_y(th).T - vt, nt)
+    fd = (r(eps) - r(-eps)) / (2 * eps)
+    assert np.allclose(fd, np.cross(vs, nt)[:, 1], atol=1e-6)

@@ -1,0 +1,248 @@
+// grid.cuh — the scene's nearest-neighbour structure and the device-side search that replaces the
+// reference's FLANN KD-tree descent (O3D/src/Core/Geometry/KDTreeFlann.cpp:165-189 ->
+// O3D/3rdparty/flann/algorithms/kdtree_single_index.h:593-642).
+//
+// Layout in HBM (all arrays in "sorted order": by coarse cell, then fine cell, then original index):
+//   hi   float4[N]  (x-ctr, y-ctr, z-ctr) rounded to f32, w = original index bits   16 B/pt  screening
+//   xyz  double[3N] exact coordinates                                              24 B/pt  decisions
+//   nrm  double[3N] exact normals (optional)                                       24 B/pt  estimator
+//   orig int[N]     sorted position -> original index                               4 B/pt
+//   coarse CoarseCell[ncoarse]  {64-bit occupancy mask of the 4x4x4 fine cells, base into fstart} 16 B
+//   fstart int[nfine+1]         start position of every OCCUPIED fine cell
+// Coarse cell edge = max query radius, fine cell edge = 1/4 of it; a radius query touches at most 3x3x3
+// coarse cells and each is one 16-byte load + a mask test.
+//
+// Exactness: candidates are screened with f32 distances on `hi` (coalescable float4 loads); every
+// decision that could differ from the reference's double arithmetic — the winner among near-ties and the
+// strict `d2 < (double)(float)(r*r)` acceptance — is re-taken in double on `xyz` using a rigorous error
+// band on the f32 distance (see band()).
+#pragma once
+
+#include <math.h>
+
+#include "common.cuh"
+
+namespace vb {
+
+struct __align__(16) CoarseCell {
+    unsigned long long mask;  // bit (fx + 4 fy + 16 fz) set iff that fine cell holds points
+    int base;                 // index into fstart of this coarse cell's first occupied fine cell
+    int pad;
+};
+
+struct GridParams {
+    double lo[3];       // corner of fine cell (0,0,0)
+    double ctr[3];      // subtracted before rounding coordinates to f32
+    double inv_fine;    // 1 / fine cell edge
+    double cell;        // coarse cell edge (>= max radius)
+    int fdim[3];        // grid size in fine cells (= 4 * coarse dims)
+    int cdim[3];        // grid size in coarse cells
+    float fine;         // fine cell edge, f32
+    // |d32 - d2| <= band_a*sqrt(d32) + band_b + band_rel*d32 for every candidate/query pair in the grid
+    float band_a, band_b, band_rel;
+};
+
+struct GridDev {
+    GridParams p;
+    const CoarseCell *coarse;
+    const int *fstart;
+    const float4 *hi;
+    const double *xyz;
+    const double *nrm;  // nullable
+    const int *orig;
+    int64_t n;
+};
+
+// f32 upper bound of the acceptance threshold r2 including the screening band (host side)
+inline float r2_upper_bound(const GridParams &g, double r2) {
+    float f = (float)(r2 * (1.0 + 1e-6));
+    float bnd = g.band_a * sqrtf(f) + g.band_b + g.band_rel * f;
+    f = f + 1.5f * bnd;
+    return nextafterf(f, 3.0e38f);
+}
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float band(const GridParams &g, float d32) {
+    return fmaf(g.band_a, sqrtf(d32), fmaf(g.band_rel, d32, g.band_b));
+}
+
+// flann::L2<double> on 3-D data: ((dx*dx) + dy*dy) + dz*dz with every operation rounded separately
+// (O3D/3rdparty/flann/algorithms/dist.h:150-177) — no FMA contraction so d2 is bit-identical to the CPU.
+__device__ __forceinline__ double l2_exact(double qx, double qy, double qz, const double *__restrict__ t) {
+    double dx = __dsub_rn(qx, t[0]), dy = __dsub_rn(qy, t[1]), dz = __dsub_rn(qz, t[2]);
+    double r = __dmul_rn(dx, dx);
+    r = __dadd_rn(r, __dmul_rn(dy, dy));
+    r = __dadd_rn(r, __dmul_rn(dz, dz));
+    return r;
+}
+
+struct QueryCtx {
+    float qx, qy, qz;  // centred f32 query
+    float fx, fy, fz;  // position inside the home fine cell, in fine-cell units [0,1)
+    int gx, gy, gz;    // home fine cell
+};
+
+// Returns false when the query is farther than one coarse cell outside the grid (cannot match).
+__device__ __forceinline__ bool make_query(const GridParams &g, double x, double y, double z, QueryCtx &c) {
+    double ux = (x - g.lo[0]) * g.inv_fine, uy = (y - g.lo[1]) * g.inv_fine, uz = (z - g.lo[2]) * g.inv_fine;
+    // the negated comparisons also reject NaN
+    if (!(ux >= 0.0 && uy >= 0.0 && uz >= 0.0 && ux < (double)g.fdim[0] && uy < (double)g.fdim[1] &&
+          uz < (double)g.fdim[2]))
+        return false;
+    double fx = floor(ux), fy = floor(uy), fz = floor(uz);
+    c.gx = (int)fx; c.gy = (int)fy; c.gz = (int)fz;
+    c.fx = (float)(ux - fx); c.fy = (float)(uy - fy); c.fz = (float)(uz - fz);
+    c.qx = (float)(x - g.ctr[0]); c.qy = (float)(y - g.ctr[1]); c.qz = (float)(z - g.ctr[2]);
+    return true;
+}
+
+// squared distance (fine-cell units) from the query to fine cell at integer offset o along one axis
+__device__ __forceinline__ float axis_gap(int o, float frac) {
+    float a = o > 0 ? (float)o - frac : (o < 0 ? frac - (float)(o + 1) : 0.0f);
+    return a;
+}
+
+__device__ __forceinline__ unsigned long long range_mask(int ax, int bx, int ay, int by, int az, int bz) {
+    // bits with fx in [ax,bx], fy in [ay,by], fz in [az,bz]; all in 0..3, a <= b
+    unsigned long long xm = (unsigned long long)((1u << (bx + 1)) - (1u << ax)) * 0x1111111111111111ull;
+    unsigned long long ym = (unsigned long long)((1u << (4 * (by + 1))) - (1u << (4 * ay))) * 0x0001000100010001ull;
+    unsigned long long zhi = bz == 3 ? ~0ull : ((1ull << (16 * (bz + 1))) - 1ull);
+    unsigned long long zm = zhi & ~((1ull << (16 * az)) - 1ull);
+    return xm & ym & zm;
+}
+
+// ---- f32 screening walk ------------------------------------------------------------------------------
+// On return: bs = sorted position of the f32-nearest candidate (or -1), best = its f32 d2,
+// second = f32 d2 of the runner-up (or the initial bound).  `bound` = f32 upper bound of the acceptance
+// threshold including its band.
+struct Screen {
+    float best, second;
+    int bs;
+};
+
+__device__ __forceinline__ void scan_run(const float4 *__restrict__ hi, int s0, int s1, const QueryCtx &c,
+                                         Screen &r) {
+    for (int s = s0; s < s1; ++s) {
+        float4 t = __ldg(hi + s);
+        float dx = c.qx - t.x, dy = c.qy - t.y, dz = c.qz - t.z;
+        float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d < r.best) {
+            r.second = r.best;
+            r.best = d;
+            r.bs = s;
+        } else {
+            r.second = fminf(r.second, d);
+        }
+    }
+}
+
+template <class Visit>
+__device__ __forceinline__ void walk_cells(const GridDev &G, const QueryCtx &c, float reach2_metric,
+                                           bool skip_home, Visit &&visit) {
+    // `visit(s0, s1, gap2_metric)` is called for every occupied fine cell whose box lies within
+    // sqrt(reach2_metric) of the query at call time; the visitor re-checks against its current best.
+    const GridParams &g = G.p;
+    const float fine = g.fine;
+    // reach in fine-cell units, padded: never prune a cell that could hold a closer point
+    float rho = sqrtf(reach2_metric) / fine * 1.00001f + 1e-6f;
+    int lx = -(int)ceilf(fmaxf(rho - c.fx, 0.0f)), hx = (int)ceilf(fmaxf(rho - (1.0f - c.fx), 0.0f));
+    int ly = -(int)ceilf(fmaxf(rho - c.fy, 0.0f)), hy = (int)ceilf(fmaxf(rho - (1.0f - c.fy), 0.0f));
+    int lz = -(int)ceilf(fmaxf(rho - c.fz, 0.0f)), hz = (int)ceilf(fmaxf(rho - (1.0f - c.fz), 0.0f));
+    int fx0 = max(c.gx + lx, 0), fx1 = min(c.gx + hx, g.fdim[0] - 1);
+    int fy0 = max(c.gy + ly, 0), fy1 = min(c.gy + hy, g.fdim[1] - 1);
+    int fz0 = max(c.gz + lz, 0), fz1 = min(c.gz + hz, g.fdim[2] - 1);
+    const int hcx = c.gx >> 2, hcy = c.gy >> 2, hcz = c.gz >> 2;
+    const int hbit = (c.gx & 3) + 4 * (c.gy & 3) + 16 * (c.gz & 3);
+    const float fine2 = fine * fine;
+    for (int cz = fz0 >> 2; cz <= (fz1 >> 2); ++cz)
+        for (int cy = fy0 >> 2; cy <= (fy1 >> 2); ++cy)
+            for (int cx = fx0 >> 2; cx <= (fx1 >> 2); ++cx) {
+                const CoarseCell cc = G.coarse[((int64_t)cz * g.cdim[1] + cy) * g.cdim[0] + cx];
+                unsigned long long m = cc.mask;
+                if (m == 0ull) continue;
+                int ax = max(fx0 - 4 * cx, 0), bx = min(fx1 - 4 * cx, 3);
+                int ay = max(fy0 - 4 * cy, 0), by = min(fy1 - 4 * cy, 3);
+                int az = max(fz0 - 4 * cz, 0), bz = min(fz1 - 4 * cz, 3);
+                unsigned long long sel = m & range_mask(ax, bx, ay, by, az, bz);
+                if (skip_home && cx == hcx && cy == hcy && cz == hcz) sel &= ~(1ull << hbit);
+                while (sel) {
+                    int b = __ffsll((long long)sel) - 1;
+                    sel &= sel - 1ull;
+                    int ox = 4 * cx + (b & 3) - c.gx, oy = 4 * cy + ((b >> 2) & 3) - c.gy,
+                        oz = 4 * cz + (b >> 4) - c.gz;
+                    float gx = axis_gap(ox, c.fx), gy = axis_gap(oy, c.fy), gz = axis_gap(oz, c.fz);
+                    // lower bound of the squared distance to anything in that cell (metric), deflated
+                    float gap2 = (gx * gx + gy * gy + gz * gz) * fine2 * 0.9999f - 1e-12f * fine2;
+                    int rank = __popcll(m & ((1ull << b) - 1ull));
+                    int s0 = __ldg(G.fstart + cc.base + rank), s1 = __ldg(G.fstart + cc.base + rank + 1);
+                    visit(s0, s1, gap2);
+                }
+            }
+}
+
+// Full radius-bounded 1-NN for one query.  r2 = (double)(float)(radius*radius), r2_ub = f32 bound
+// >= r2 + band.  Returns sorted position of the accepted neighbour or -1; d2 = exact double distance.
+static __device__ __noinline__ int nn_exact_rescan(const GridDev &G, const QueryCtx &c, double qx, double qy,
+                                            double qz, double r2, float reach2, double *d2_out) {
+    // Rare path (near-tie between candidates, or winner within the band of the threshold): redo the walk
+    // in double.  Ties break to the lowest ORIGINAL index (documented rule; FLANN's is traversal order).
+    double bd = r2;
+    int bs = -1, bo = 0x7fffffff;
+    auto visit = [&](int s0, int s1, float gap2) {
+        if ((double)gap2 > bd) return;
+        for (int s = s0; s < s1; ++s) {
+            double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)s);
+            if (d < bd) {
+                bd = d; bs = s; bo = __ldg(G.orig + s);
+            } else if (d == bd && bs >= 0) {
+                int o = __ldg(G.orig + s);
+                if (o < bo) { bs = s; bo = o; }
+            }
+        }
+    };
+    walk_cells(G, c, reach2, false, visit);
+    *d2_out = bs >= 0 ? bd : 0.0;
+    return bs;
+}
+
+__device__ __forceinline__ int nn_search(const GridDev &G, const QueryCtx &c, double qx, double qy, double qz,
+                                         double r2, float r2_ub, double *d2_out) {
+    const GridParams &g = G.p;
+    Screen r;
+    r.best = r2_ub; r.second = 3.0e38f; r.bs = -1;
+    // 1. home fine cell first: gives a tight bound that prunes almost everything else
+    {
+        const int hcx = c.gx >> 2, hcy = c.gy >> 2, hcz = c.gz >> 2;
+        const CoarseCell cc = G.coarse[((int64_t)hcz * g.cdim[1] + hcy) * g.cdim[0] + hcx];
+        const int hbit = (c.gx & 3) + 4 * (c.gy & 3) + 16 * (c.gz & 3);
+        if ((cc.mask >> hbit) & 1ull) {
+            int rank = __popcll(cc.mask & ((1ull << hbit) - 1ull));
+            int s0 = __ldg(G.fstart + cc.base + rank), s1 = __ldg(G.fstart + cc.base + rank + 1);
+            scan_run(G.hi, s0, s1, c, r);
+        }
+    }
+    // 2. every other fine cell within reach of the current bound.  The runner-up matters too (ambiguity
+    //    test), so the reach covers second-best candidates inside the band of the best.
+    float reach2 = fminf(r.best + 2.0f * band(g, r.best), r2_ub);
+    auto visit = [&](int s0, int s1, float gap2) {
+        if (gap2 > fminf(r.best + 2.0f * band(g, r.best), r2_ub)) return;
+        scan_run(G.hi, s0, s1, c, r);
+    };
+    walk_cells(G, c, reach2, true, visit);
+    if (r.bs < 0) { *d2_out = 0.0; return -1; }
+    // 3. decide in double
+    float bb = band(g, r.best);
+    if (r.second - r.best > bb + band(g, r.second)) {
+        // unique f32 winner, and (second starts at r2_ub) it is also clear of the threshold band
+        double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)r.bs);
+        if (d < r2) { *d2_out = d; return r.bs; }
+        *d2_out = 0.0;
+        return -1;
+    }
+    return nn_exact_rescan(G, c, qx, qy, qz, r2, fminf(r.best + 2.0f * bb, r2_ub), d2_out);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace vb

@@ -1,0 +1,812 @@
+// icp.cu — the batched ICP operator: correspondence search fused with the estimator's reductions, the
+// small solves, and the convergence loop, all resident on the GPU.
+//
+// Reference path replaced (O3D = thirdparty/Open3D):
+//   open3d::RegistrationICP                         O3D/src/Core/Registration/Registration.cpp:141-186
+//   GetRegistrationResultAndCorrespondences         Registration.cpp:41-96      } k_pass: one launch does
+//   PointCloud::Transform                           Geometry/PointCloud.cpp:75-87 } transform + 1-NN + the
+//   TransformationEstimationPointToPlane rows       TransformationEstimation.cpp:82-90 } per-correspondence
+//   ComputeJTJandJTr                                Utility/Eigen.cpp:137-182   } products + block reduction
+//   TransformationEstimationPointToPoint / cicp     TransformationEstimation.cpp:47-59, src/constrained_ICP.cpp:25-37
+//   SolveJacobianSystemAndObtainExtrinsicMatrix     Utility/Eigen.cpp:88-106    } k_solve: one thread per
+//   Eigen::umeyama                                  3rdparty/Eigen/.../Umeyama.h:93-162 } problem, fixed-order reduce
+//   feh::RegisterModelToScene                       src/annotation.cpp:29-64
+//
+// Differences from the reference that are by design:
+//   - the accumulated transform is applied to the ORIGINAL source points each iteration instead of
+//     transforming the cloud incrementally (Registration.cpp:175): one read, no write, no drift;
+//   - correspondences are never materialised between the search and the estimator (the reference writes a
+//     CorrespondenceSet and re-gathers it): the matched target point/normal are consumed in registers;
+//   - reductions have a fixed order (warp halving tree -> warps -> blocks), so results are deterministic;
+//     the reference's OpenMP merge order is thread-arrival order.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "linalg.cuh"
+#include "scene.cuh"
+#include "sort.cuh"
+
+namespace vb {
+
+namespace {
+
+constexpr int kPassTpb = 256;
+constexpr int kPtsPerThread = 4;
+constexpr int kChunk = kPassTpb * kPtsPerThread;  // source points per block
+constexpr int kAcc = 32;                          // accumulator slots (padded)
+constexpr int kBuckets = 32768;                   // spatial buckets per source cloud (15-bit key)
+
+// accumulator slots, MODE 1 (point-to-plane): 0..20 JTJ upper triangle row-major, 21..26 JTr
+// MODE 0 (point-to-point): 0..2 sum s', 3..5 sum d', 6..14 sum d' s'^T (row-major), 15 sum |s'|^2
+// both: 30 = sum d2 (exact NN distances), 31 = count
+constexpr int kSlotD2 = 30, kSlotCount = 31;
+
+struct ProbState {
+    double T[16];
+    double fitness, rmse, prev_fitness, prev_rmse;
+    int ncorr, iters, done, pad;
+};
+
+struct BlockTask {
+    int prob;       // problem index
+    int src_begin;  // first source point (global sorted position)
+    int count;      // points in this block's chunk
+    int corr_begin; // where this chunk's matches go in corr_j
+};
+
+struct ProbDesc {
+    int cloud;
+    int npts;
+    int blk_begin, blk_count;
+    int src_begin;
+    int corr_begin;
+};
+
+struct PassParams {
+    double r2;    // (double)(float)(max_dist^2)  (KDTreeFlann.cpp:185)
+    float r2_ub;  // f32 upper bound of r2 including the screening band
+};
+
+struct SolveParams {
+    double rel_fitness, rel_rmse;
+    double g[3];
+    int max_iter;
+    int estimator;
+};
+
+// ---- warp-level vector reduction: 32 slots over 32 lanes in 31 exchange steps (recursive halving).
+// After the call lane L holds the warp total of slot L.  Fixed order => deterministic.
+__device__ __forceinline__ double warp_reduce_slots(double (&v)[kAcc]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int j = 0; j < h; j++) {
+            double send = up ? v[j] : v[j + h];
+            double keep = up ? v[j + h] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return v[0];
+}
+
+template <int MODE>
+__device__ __forceinline__ void contributions(bool matched, double d2, const double *vs, const double *vt,
+                                              const double *nt, const double *cref, double (&v)[kAcc]) {
+#pragma unroll
+    for (int j = 0; j < kAcc; j++) v[j] = 0.0;
+    if (!matched) return;
+    if (MODE == 1) {
+        // r = (vs - vt).nt ; J = [vs x nt ; nt]  (TransformationEstimation.cpp:87-89)
+        double r = (vs[0] - vt[0]) * nt[0] + (vs[1] - vt[1]) * nt[1] + (vs[2] - vt[2]) * nt[2];
+        double J[6] = {vs[1] * nt[2] - vs[2] * nt[1], vs[2] * nt[0] - vs[0] * nt[2],
+                       vs[0] * nt[1] - vs[1] * nt[0], nt[0], nt[1], nt[2]};
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = a; b < 6; b++) v[k++] = J[a] * J[b];
+#pragma unroll
+        for (int a = 0; a < 6; a++) v[21 + a] = J[a] * r;
+    } else {
+        // moments of (s', d') = (vs - c, vt - c): enough for Eigen::umeyama's means, Sigma and src_var
+        double s[3] = {vs[0] - cref[0], vs[1] - cref[1], vs[2] - cref[2]};
+        double d[3] = {vt[0] - cref[0], vt[1] - cref[1], vt[2] - cref[2]};
+#pragma unroll
+        for (int a = 0; a < 3; a++) { v[a] = s[a]; v[3 + a] = d[a]; }
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) v[6 + 3 * a + b] = d[a] * s[b];
+        v[15] = s[0] * s[0] + s[1] * s[1] + s[2] * s[2];
+    }
+    v[kSlotD2] = d2;
+    v[kSlotCount] = 1.0;
+}
+
+// One ICP correspondence pass for every active problem: transform + radius-bounded 1-NN + estimator
+// products + block reduction.  grid = one block per kChunk source points of one problem.
+template <int MODE>
+__global__ void __launch_bounds__(kPassTpb) k_pass(GridDev G, const double *__restrict__ src_xyz,
+                                                   const BlockTask *__restrict__ tasks,
+                                                   const ProbState *__restrict__ states,
+                                                   double *__restrict__ partials, int *__restrict__ corr_j,
+                                                   PassParams pp) {
+    const BlockTask task = tasks[blockIdx.x];
+    const ProbState *st = states + task.prob;
+    if (st->done) return;
+    __shared__ double sT[12];
+    __shared__ double swarp[kPassTpb / 32][kAcc];
+    if (threadIdx.x < 12) sT[threadIdx.x] = st->T[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double T[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) T[i] = sT[i];
+    // cref = translation part of T: keeps the p2p moments O(object size) instead of O(scene size)
+    const double cref[3] = {T[3], T[7], T[11]};
+    double acc = 0.0;  // lane L accumulates slot L
+#pragma unroll 1
+    for (int k = 0; k < kPtsPerThread; k++) {
+        const int local = k * kPassTpb + threadIdx.x;
+        const bool valid = local < task.count;
+        bool matched = false;
+        double d2 = 0.0, vs[3] = {0, 0, 0}, vt[3] = {0, 0, 0}, nt[3] = {0, 0, 0};
+        if (valid) {
+            const double *p = src_xyz + 3 * (int64_t)(task.src_begin + local);
+            const double px = p[0], py = p[1], pz = p[2];
+            vs[0] = T[0] * px + T[1] * py + T[2] * pz + T[3];
+            vs[1] = T[4] * px + T[5] * py + T[6] * pz + T[7];
+            vs[2] = T[8] * px + T[9] * py + T[10] * pz + T[11];
+            QueryCtx c;
+            int bs = -1;
+            if (make_query(G.p, vs[0], vs[1], vs[2], c))
+                bs = nn_search(G, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, &d2);
+            matched = bs >= 0;
+            int j = -1;
+            if (matched) {
+                j = __ldg(G.orig + bs);
+                const double *t = G.xyz + 3 * (int64_t)bs;
+                vt[0] = t[0]; vt[1] = t[1]; vt[2] = t[2];
+                if (MODE == 1) {
+                    const double *nn = G.nrm + 3 * (int64_t)bs;
+                    nt[0] = nn[0]; nt[1] = nn[1]; nt[2] = nn[2];
+                }
+            }
+            corr_j[task.corr_begin + local] = j;
+        }
+        double v[kAcc];
+        contributions<MODE>(matched, d2, vs, vt, nt, cref, v);
+        acc += warp_reduce_slots(v);
+    }
+    swarp[warp][lane] = acc;
+    __syncthreads();
+    if (threadIdx.x < kAcc) {
+        double s = swarp[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < kPassTpb / 32; w++) s += swarp[w][threadIdx.x];
+        partials[(int64_t)blockIdx.x * kAcc + threadIdx.x] = s;
+    }
+}
+
+// ---- estimator solves from the reduced slots ---------------------------------------------------------
+__device__ void update_p2plane(const double *tot, const SolveParams &sp, double *U) {
+    mat4_identity(U);
+    double JTJ[36], JTr[6];
+    int k = 0;
+    for (int a = 0; a < 6; a++)
+        for (int b = a; b < 6; b++) { JTJ[6 * a + b] = tot[k]; JTJ[6 * b + a] = tot[k]; k++; }
+    for (int a = 0; a < 6; a++) JTr[a] = tot[21 + a];
+    if (sp.estimator == VB200_EST_P2PLANE) {
+        double x[6];
+        if (solve_normal_equations<6>(JTJ, JTr, x)) vec6_to_T(x, U);  // else Identity (TransformationEstimation.cpp:102)
+    } else {
+        // gravity-constrained: J4 = [(vs x nt).g ; nt] = P J6 with P = [[g^T 0],[0 I]]  =>  A4 = P JTJ P^T
+        const double *g = sp.g;
+        double A[16], b[4];
+        double Mg[6];  // JTJ[:, 0:3] * g
+        for (int r = 0; r < 6; r++) Mg[r] = JTJ[6 * r + 0] * g[0] + JTJ[6 * r + 1] * g[1] + JTJ[6 * r + 2] * g[2];
+        A[0] = g[0] * Mg[0] + g[1] * Mg[1] + g[2] * Mg[2];
+        for (int c = 0; c < 3; c++) { A[1 + c] = Mg[3 + c]; A[4 * (1 + c)] = Mg[3 + c]; }
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) A[4 * (1 + r) + 1 + c] = JTJ[6 * (3 + r) + 3 + c];
+        b[0] = g[0] * JTr[0] + g[1] * JTr[1] + g[2] * JTr[2];
+        for (int c = 0; c < 3; c++) b[1 + c] = JTr[3 + c];
+        double x[4];
+        if (solve_normal_equations<4>(A, b, x)) axis_angle_to_T(x[0], g, x + 1, U);
+    }
+}
+
+__device__ void update_p2p(const double *tot, const double *cref, double *U) {
+    mat4_identity(U);
+    const double K = tot[kSlotCount];
+    if (!(K > 0.0)) return;  // corres.empty() -> Identity (TransformationEstimation.cpp:51)
+    const double inv = 1.0 / K;
+    double ms[3], md[3], Sigma[9];
+    for (int a = 0; a < 3; a++) { ms[a] = tot[a] * inv; md[a] = tot[3 + a] * inv; }
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) Sigma[3 * a + b] = tot[6 + 3 * a + b] * inv - md[a] * ms[b];
+    double R[9];
+    kabsch_rotation(Sigma, R, nullptr);
+    // t = mu_d - R mu_s with mu = cref + mu'
+    for (int r = 0; r < 3; r++) {
+        double mus[3] = {cref[0] + ms[0], cref[1] + ms[1], cref[2] + ms[2]};
+        U[4 * r + 0] = R[3 * r + 0]; U[4 * r + 1] = R[3 * r + 1]; U[4 * r + 2] = R[3 * r + 2];
+        U[4 * r + 3] = (cref[r] + md[r]) - (R[3 * r] * mus[0] + R[3 * r + 1] * mus[1] + R[3 * r + 2] * mus[2]);
+    }
+}
+
+// One block per problem: fixed-order reduction of the pass partials, result bookkeeping, convergence test
+// (Registration.cpp:179-183) and the estimator update T <- update * T (Registration.cpp:172-174).
+__global__ void __launch_bounds__(256) k_solve(const ProbDesc *__restrict__ probs, ProbState *__restrict__ states,
+                                               const double *__restrict__ partials, SolveParams sp,
+                                               int pass_index) {
+    const ProbDesc pd = probs[blockIdx.x];
+    ProbState *st = states + blockIdx.x;
+    if (st->done) return;
+    __shared__ double sw[8][kAcc];
+    __shared__ double tot[kAcc];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double s = 0.0;
+    for (int b = warp; b < pd.blk_count; b += 8) s += partials[(int64_t)(pd.blk_begin + b) * kAcc + lane];
+    sw[warp][lane] = s;
+    __syncthreads();
+    if (threadIdx.x < kAcc) {
+        double t = sw[0][threadIdx.x];
+        for (int w = 1; w < 8; w++) t += sw[w][threadIdx.x];
+        tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const double K = tot[kSlotCount];
+    double fitness = 0.0, rmse = 0.0;
+    if (K > 0.0 && pd.npts > 0) {  // Registration.cpp:87-93
+        fitness = K / (double)pd.npts;
+        rmse = sqrt(tot[kSlotD2] / K);
+    }
+    st->fitness = fitness;
+    st->rmse = rmse;
+    st->ncorr = (int)K;
+    if (pass_index >= 1 && fabs(st->prev_fitness - fitness) < sp.rel_fitness &&
+        fabs(st->prev_rmse - rmse) < sp.rel_rmse) {
+        st->done = 1;
+        return;
+    }
+    st->prev_fitness = fitness;
+    st->prev_rmse = rmse;
+    if (pass_index >= sp.max_iter) {
+        st->done = 1;
+        return;
+    }
+    double U[16], T[16];
+    for (int i = 0; i < 16; i++) T[i] = st->T[i];
+    if (sp.estimator == VB200_EST_P2P) {
+        const double cref[3] = {T[3], T[7], T[11]};
+        update_p2p(tot, cref, U);
+    } else {
+        update_p2plane(tot, sp, U);
+    }
+    mat4_mul(U, T, T);
+    for (int i = 0; i < 16; i++) st->T[i] = T[i];
+    st->iters = pass_index + 1;
+}
+
+// ---- source-cloud bucket sort (spatial coherence for the search; deterministic order) ----------------
+__device__ __forceinline__ int find_cloud(const int *__restrict__ off, int ncloud, int i) {
+    int lo = 0, hi = ncloud;  // off[lo] <= i < off[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) k_src_keys(const double *__restrict__ xyz, int n,
+                                                  const int *__restrict__ cloud_off, int ncloud,
+                                                  double inv_half_cell, int *__restrict__ key,
+                                                  int *__restrict__ counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = find_cloud(cloud_off, ncloud, i);
+    // 5 bits per axis of the half-coarse-cell index in the cloud's own frame: neighbours in space share
+    // or neighbour buckets whatever rigid transform is applied later
+    int kx = (int)floor(xyz[3 * (int64_t)i] * inv_half_cell) & 31;
+    int ky = (int)floor(xyz[3 * (int64_t)i + 1] * inv_half_cell) & 31;
+    int kz = (int)floor(xyz[3 * (int64_t)i + 2] * inv_half_cell) & 31;
+    int kk = c * kBuckets + ((kz * 32 + ky) * 32 + kx);
+    key[i] = kk;
+    atomicAdd(counts + kk, 1);
+}
+
+__global__ void __launch_bounds__(256) k_src_scatter(const int *__restrict__ key, int n,
+                                                     const int *__restrict__ start, int *__restrict__ cursor,
+                                                     int *__restrict__ sidx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int kk = key[i];
+    sidx[start[kk] + atomicAdd(cursor + kk, 1)] = i;
+}
+
+__global__ void __launch_bounds__(128) k_src_sort_buckets(int nbuckets, const int *__restrict__ start,
+                                                          int *__restrict__ sidx) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    int s0 = start[b], s1 = start[b + 1];
+    if (s1 - s0 > 1) cell_sort(sidx + s0, s1 - s0);
+}
+
+__global__ void __launch_bounds__(256) k_src_gather(const double *__restrict__ in, int n,
+                                                    const int *__restrict__ sidx,
+                                                    const int *__restrict__ cloud_off, int ncloud,
+                                                    double *__restrict__ out, int *__restrict__ orig) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int i = sidx[s];
+    out[3 * (int64_t)s] = in[3 * (int64_t)i];
+    out[3 * (int64_t)s + 1] = in[3 * (int64_t)i + 1];
+    out[3 * (int64_t)s + 2] = in[3 * (int64_t)i + 2];
+    orig[s] = i - cloud_off[find_cloud(cloud_off, ncloud, i)];
+}
+
+// ---- estimator plug-in kernel: reductions over an explicit correspondence list ------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kPassTpb) k_estimate(const double *__restrict__ vs_in,
+                                                       const double *__restrict__ vt_in,
+                                                       const double *__restrict__ nt_in, int64_t K,
+                                                       double *__restrict__ partials) {
+    __shared__ double swarp[kPassTpb / 32][kAcc];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double cref[3] = {vs_in[0], vs_in[1], vs_in[2]};
+    double acc = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < kPtsPerThread; k++) {
+        int64_t i = (int64_t)blockIdx.x * kChunk + k * kPassTpb + threadIdx.x;
+        bool valid = i < K;
+        double vs[3] = {0, 0, 0}, vt[3] = {0, 0, 0}, nt[3] = {0, 0, 0};
+        if (valid) {
+            for (int a = 0; a < 3; a++) {
+                vs[a] = vs_in[3 * i + a];
+                vt[a] = vt_in[3 * i + a];
+                if (MODE == 1) nt[a] = nt_in[3 * i + a];
+            }
+        }
+        double v[kAcc];
+        contributions<MODE>(valid, 0.0, vs, vt, nt, cref, v);
+        acc += warp_reduce_slots(v);
+    }
+    swarp[warp][lane] = acc;
+    __syncthreads();
+    if (threadIdx.x < kAcc) {
+        double s = swarp[0][threadIdx.x];
+        for (int w = 1; w < kPassTpb / 32; w++) s += swarp[w][threadIdx.x];
+        partials[(int64_t)blockIdx.x * kAcc + threadIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_estimate_solve(const double *__restrict__ partials, int nblk,
+                                                        const double *__restrict__ vs_in, SolveParams sp,
+                                                        double *__restrict__ out_T) {
+    __shared__ double sw[8][kAcc];
+    __shared__ double tot[kAcc];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double s = 0.0;
+    for (int b = warp; b < nblk; b += 8) s += partials[(int64_t)b * kAcc + lane];
+    sw[warp][lane] = s;
+    __syncthreads();
+    if (threadIdx.x < kAcc) {
+        double t = sw[0][threadIdx.x];
+        for (int w = 1; w < 8; w++) t += sw[w][threadIdx.x];
+        tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    double U[16];
+    if (sp.estimator == VB200_EST_P2P) {
+        const double cref[3] = {vs_in[0], vs_in[1], vs_in[2]};
+        update_p2p(tot, cref, U);
+    } else {
+        update_p2plane(tot, sp, U);
+    }
+    for (int i = 0; i < 16; i++) out_T[i] = U[i];
+}
+
+}  // namespace
+
+// ======================================================================================================
+struct Batch {
+    Scene *scene = nullptr;
+    int ncloud = 0;
+    int64_t npts = 0;
+    std::vector<int> cloud_off;     // host copy, ncloud+1
+    bool has_normals = false;
+    double *d_src = nullptr;        // sorted source points, 3*npts
+    int *d_src_orig = nullptr;      // sorted position -> original index local to its cloud
+    int *d_cloud_off = nullptr;
+    // problems
+    int P = 0;
+    std::vector<ProbDesc> probs;
+    int nblk = 0;
+    int64_t ncorr_slots = 0;
+    ProbDesc *d_probs = nullptr;
+    ProbState *d_states = nullptr;
+    BlockTask *d_tasks = nullptr;
+    double *d_partials = nullptr;
+    int *d_corr = nullptr;
+    int64_t launches = 0;
+};
+
+static void batch_free_problems(Batch *b) {
+    cudaFree(b->d_probs); cudaFree(b->d_states); cudaFree(b->d_tasks); cudaFree(b->d_partials); cudaFree(b->d_corr);
+    b->d_probs = nullptr; b->d_states = nullptr; b->d_tasks = nullptr; b->d_partials = nullptr; b->d_corr = nullptr;
+    b->P = 0; b->nblk = 0; b->probs.clear();
+}
+
+static void batch_free(Batch *b) {
+    if (!b) return;
+    batch_free_problems(b);
+    cudaFree(b->d_src); cudaFree(b->d_src_orig); cudaFree(b->d_cloud_off);
+    delete b;
+}
+
+static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int ncloud) {
+    Scene *sc = b->scene;
+    cudaStream_t st = sc->stream;
+    b->ncloud = ncloud;
+    b->cloud_off.resize((size_t)ncloud + 1);
+    for (int c = 0; c <= ncloud; c++) {
+        int64_t o = off[c] - off[0];
+        if (o < 0 || o > 0x7fffffff || (c > 0 && off[c] < off[c - 1])) return VB200_ERR_INVALID;
+        b->cloud_off[c] = (int)o;
+    }
+    const int n = b->cloud_off[ncloud];
+    b->npts = n;
+    VB_CUDA(cudaMalloc((void **)&b->d_cloud_off, sizeof(int) * ((size_t)ncloud + 1)));
+    VB_CUDA(cudaMemcpyAsync(b->d_cloud_off, b->cloud_off.data(), sizeof(int) * ((size_t)ncloud + 1),
+                            cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMalloc((void **)&b->d_src, sizeof(double) * 3 * (size_t)std::max(n, 1)));
+    VB_CUDA(cudaMalloc((void **)&b->d_src_orig, sizeof(int) * (size_t)std::max(n, 1)));
+    if (n == 0) return VB200_OK;
+    DevBuf<double> d_in;
+    DevBuf<int> d_key, d_counts, d_start, d_sidx;
+    const size_t nb = (size_t)ncloud * kBuckets + 1;
+    VB_CUDA(d_in.alloc(3 * (size_t)n));
+    VB_CUDA(d_key.alloc((size_t)n));
+    VB_CUDA(d_sidx.alloc((size_t)n));
+    VB_CUDA(d_counts.alloc(nb));
+    VB_CUDA(d_start.alloc(nb));
+    VB_CUDA(cudaMemcpyAsync(d_in.p, src_xyz + 3 * off[0], sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMemsetAsync(d_counts.p, 0, sizeof(int) * nb, st));
+    const double inv_half = 2.0 / sc->grid.p.cell;
+    k_src_keys<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, b->d_cloud_off, ncloud, inv_half, d_key.p, d_counts.p);
+    VB_TRY(exclusive_scan_i32(d_counts.p, d_start.p, (int64_t)nb, nullptr, st));
+    VB_CUDA(cudaMemsetAsync(d_counts.p, 0, sizeof(int) * nb, st));
+    k_src_scatter<<<div_up(n, 256), 256, 0, st>>>(d_key.p, n, d_start.p, d_counts.p, d_sidx.p);
+    k_src_sort_buckets<<<div_up((int64_t)nb - 1, 128), 128, 0, st>>>((int)nb - 1, d_start.p, d_sidx.p);
+    k_src_gather<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, d_sidx.p, b->d_cloud_off, ncloud, b->d_src, b->d_src_orig);
+    VB_CUDA(cudaGetLastError());
+    b->launches += 4 + 3;
+    VB_CUDA(cudaStreamSynchronize(st));  // temporaries are released on return
+    return VB200_OK;
+}
+
+static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *init_T, int P) {
+    cudaStream_t st = b->scene->stream;
+    batch_free_problems(b);
+    b->P = P;
+    b->probs.resize((size_t)P);
+    std::vector<BlockTask> tasks;
+    std::vector<ProbState> states((size_t)P);
+    int64_t corr = 0;
+    for (int p = 0; p < P; p++) {
+        int c = cloud_ids ? cloud_ids[p] : p;
+        if (c < 0 || c >= b->ncloud) return VB200_ERR_INVALID;
+        ProbDesc &pd = b->probs[p];
+        pd.cloud = c;
+        pd.npts = b->cloud_off[c + 1] - b->cloud_off[c];
+        pd.src_begin = b->cloud_off[c];
+        pd.corr_begin = (int)corr;
+        pd.blk_begin = (int)tasks.size();
+        for (int s = 0; s < pd.npts; s += kChunk) {
+            BlockTask t;
+            t.prob = p;
+            t.src_begin = pd.src_begin + s;
+            t.count = std::min(kChunk, pd.npts - s);
+            t.corr_begin = pd.corr_begin + s;
+            tasks.push_back(t);
+        }
+        pd.blk_count = (int)tasks.size() - pd.blk_begin;
+        corr += pd.npts;
+        if (corr > 0x7fffffff) return VB200_ERR_INVALID;
+        ProbState &s = states[p];
+        memset(&s, 0, sizeof(s));
+        for (int i = 0; i < 16; i++) s.T[i] = init_T[16 * (size_t)p + i];
+    }
+    b->nblk = (int)tasks.size();
+    b->ncorr_slots = corr;
+    VB_CUDA(cudaMalloc((void **)&b->d_probs, sizeof(ProbDesc) * (size_t)std::max(P, 1)));
+    VB_CUDA(cudaMalloc((void **)&b->d_states, sizeof(ProbState) * (size_t)std::max(P, 1)));
+    VB_CUDA(cudaMalloc((void **)&b->d_tasks, sizeof(BlockTask) * (size_t)std::max(b->nblk, 1)));
+    VB_CUDA(cudaMalloc((void **)&b->d_partials, sizeof(double) * kAcc * (size_t)std::max(b->nblk, 1)));
+    VB_CUDA(cudaMalloc((void **)&b->d_corr, sizeof(int) * (size_t)std::max<int64_t>(corr, 1)));
+    if (P) {
+        VB_CUDA(cudaMemcpyAsync(b->d_probs, b->probs.data(), sizeof(ProbDesc) * (size_t)P, cudaMemcpyHostToDevice, st));
+        VB_CUDA(cudaMemcpyAsync(b->d_states, states.data(), sizeof(ProbState) * (size_t)P, cudaMemcpyHostToDevice, st));
+    }
+    if (b->nblk)
+        VB_CUDA(cudaMemcpyAsync(b->d_tasks, tasks.data(), sizeof(BlockTask) * (size_t)b->nblk, cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMemsetAsync(b->d_corr, 0xff, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
+    VB_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
+    return VB200_OK;
+}
+
+
+static int batch_run(Batch *b, int estimator, const double *gravity, double max_dist, double rel_fitness,
+                     double rel_rmse, int max_iter) {
+    Scene *sc = b->scene;
+    cudaStream_t st = sc->stream;
+    if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY || max_iter < 0) return VB200_ERR_INVALID;
+    if (!(max_dist > 0.0)) return VB200_ERR_DISTANCE;
+    if (max_dist > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
+    const bool plane = estimator != VB200_EST_P2P;
+    if (plane && (!b->has_normals || !sc->has_normals)) return VB200_ERR_NORMALS;
+    if (b->P == 0) return VB200_OK;
+    PassParams pp;
+    pp.r2 = (double)(float)(max_dist * max_dist);
+    pp.r2_ub = r2_upper_bound(sc->grid.p, pp.r2);
+    SolveParams sp;
+    sp.rel_fitness = rel_fitness;
+    sp.rel_rmse = rel_rmse;
+    sp.max_iter = max_iter;
+    sp.estimator = estimator;
+    sp.g[0] = 0.0; sp.g[1] = 1.0; sp.g[2] = 0.0;  // VISMA's gravity convention: +Y (src/annotation.cpp:43,84)
+    if (estimator == VB200_EST_P2PLANE_GRAVITY && gravity) {
+        double l = sqrt(gravity[0] * gravity[0] + gravity[1] * gravity[1] + gravity[2] * gravity[2]);
+        if (!(l > 0.0)) return VB200_ERR_INVALID;
+        for (int a = 0; a < 3; a++) sp.g[a] = gravity[a] / l;
+    }
+    for (int it = 0; it <= max_iter; it++) {
+        if (b->nblk) {
+            if (plane)
+                k_pass<1><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
+            else
+                k_pass<0><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
+            b->launches++;
+        }
+        k_solve<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, sp, it);
+        b->launches++;
+    }
+    VB_CUDA(cudaGetLastError());
+    return VB200_OK;
+}
+
+}  // namespace vb
+
+// ======================================================================================================
+using vb::Batch;
+using vb::Scene;
+
+extern "C" int vb200_batch_create(vb200_scene_t *scene, const double *src_xyz, const double *src_nrm,
+                                  const int64_t *src_offsets, int32_t n_clouds, vb200_batch_t **out) {
+    if (!out) return VB200_ERR_INVALID;
+    *out = nullptr;
+    if (!scene || !src_offsets || n_clouds < 0 || (!src_xyz && src_offsets[n_clouds] > src_offsets[0]))
+        return VB200_ERR_INVALID;
+    Scene *sc = reinterpret_cast<Scene *>(scene);
+    VB_CUDA(cudaSetDevice(sc->device));
+    Batch *b = new Batch();
+    b->scene = sc;
+    b->has_normals = src_nrm != nullptr;  // only presence matters (Registration.cpp:152-157)
+    int rc = vb::batch_upload(b, src_xyz, src_offsets, n_clouds);
+    if (rc != VB200_OK) {
+        vb::batch_free(b);
+        return rc;
+    }
+    *out = reinterpret_cast<vb200_batch_t *>(b);
+    return VB200_OK;
+}
+
+extern "C" int vb200_batch_destroy(vb200_batch_t *batch) {
+    if (!batch) return VB200_OK;
+    Batch *b = reinterpret_cast<Batch *>(batch);
+    cudaSetDevice(b->scene->device);
+    cudaStreamSynchronize(b->scene->stream);
+    vb::batch_free(b);
+    return VB200_OK;
+}
+
+extern "C" int vb200_batch_set_problems(vb200_batch_t *batch, const int32_t *cloud_ids, const double *init_T,
+                                        int32_t P) {
+    if (!batch || P < 0 || (P > 0 && !init_T)) return VB200_ERR_INVALID;
+    Batch *b = reinterpret_cast<Batch *>(batch);
+    VB_CUDA(cudaSetDevice(b->scene->device));
+    return vb::batch_set_problems(b, cloud_ids, init_T, P);
+}
+
+extern "C" int vb200_batch_run(vb200_batch_t *batch, int estimator, const double *gravity_axis, double max_dist,
+                               double rel_fitness, double rel_rmse, int max_iter) {
+    if (!batch) return VB200_ERR_INVALID;
+    Batch *b = reinterpret_cast<Batch *>(batch);
+    VB_CUDA(cudaSetDevice(b->scene->device));
+    return vb::batch_run(b, estimator, gravity_axis, max_dist, rel_fitness, rel_rmse, max_iter);
+}
+
+extern "C" int vb200_batch_results(vb200_batch_t *batch, double *out_T, double *out_fitness, double *out_rmse,
+                                   int32_t *out_ncorr, int32_t *out_iters) {
+    if (!batch) return VB200_ERR_INVALID;
+    Batch *b = reinterpret_cast<Batch *>(batch);
+    VB_CUDA(cudaSetDevice(b->scene->device));
+    std::vector<vb::ProbState> states((size_t)b->P);
+    if (b->P)
+        VB_CUDA(cudaMemcpyAsync(states.data(), b->d_states, sizeof(vb::ProbState) * (size_t)b->P,
+                                cudaMemcpyDeviceToHost, b->scene->stream));
+    VB_CUDA(cudaStreamSynchronize(b->scene->stream));
+    for (int p = 0; p < b->P; p++) {
+        const vb::ProbState &s = states[p];
+        if (out_T) memcpy(out_T + 16 * (size_t)p, s.T, sizeof(double) * 16);
+        if (out_fitness) out_fitness[p] = s.fitness;
+        if (out_rmse) out_rmse[p] = s.rmse;
+        if (out_ncorr) out_ncorr[p] = s.ncorr;
+        if (out_iters) out_iters[p] = s.iters;
+    }
+    return VB200_OK;
+}
+
+extern "C" int vb200_batch_corr(vb200_batch_t *batch, int32_t p, int32_t *out_corr, int32_t *out_k) {
+    if (!batch || !out_corr || !out_k) return VB200_ERR_INVALID;
+    Batch *b = reinterpret_cast<Batch *>(batch);
+    if (p < 0 || p >= b->P) return VB200_ERR_INVALID;
+    VB_CUDA(cudaSetDevice(b->scene->device));
+    const vb::ProbDesc &pd = b->probs[p];
+    std::vector<int> cj((size_t)pd.npts), so((size_t)pd.npts);
+    if (pd.npts) {
+        VB_CUDA(cudaMemcpyAsync(cj.data(), b->d_corr + pd.corr_begin, sizeof(int) * (size_t)pd.npts,
+                                cudaMemcpyDeviceToHost, b->scene->stream));
+        VB_CUDA(cudaMemcpyAsync(so.data(), b->d_src_orig + pd.src_begin, sizeof(int) * (size_t)pd.npts,
+                                cudaMemcpyDeviceToHost, b->scene->stream));
+    }
+    VB_CUDA(cudaStreamSynchronize(b->scene->stream));
+    // sorted position -> original source index, then emit in ascending source index
+    std::vector<int> by_src((size_t)pd.npts, -1);
+    for (int s = 0; s < pd.npts; s++) by_src[(size_t)so[s]] = cj[s];
+    int k = 0;
+    for (int i = 0; i < pd.npts; i++)
+        if (by_src[i] >= 0) {
+            out_corr[2 * k] = i;
+            out_corr[2 * k + 1] = by_src[i];
+            k++;
+        }
+    *out_k = k;
+    return VB200_OK;
+}
+
+extern "C" int64_t vb200_batch_launches(const vb200_batch_t *batch) {
+    return batch ? reinterpret_cast<const Batch *>(batch)->launches : 0;
+}
+
+extern "C" int vb200_icp_run(vb200_scene_t *scene, const double *src_xyz, const double *src_nrm,
+                             const int64_t *src_offsets, int32_t B, const double *init_T, int estimator,
+                             const double *gravity_axis, double max_dist, double rel_fitness, double rel_rmse,
+                             int max_iter, double *out_T, double *out_fitness, double *out_rmse,
+                             int32_t *out_ncorr, int32_t *out_iters, int32_t *out_corr) {
+    if (!scene || !src_offsets || B < 0 || (B > 0 && !init_T)) return VB200_ERR_INVALID;
+    // the reference's early-outs return RegistrationResult(init): transformation = init, fitness = rmse = 0
+    auto passthrough = [&]() {
+        for (int p = 0; p < B; p++) {
+            if (out_T) memcpy(out_T + 16 * (size_t)p, init_T + 16 * (size_t)p, sizeof(double) * 16);
+            if (out_fitness) out_fitness[p] = 0.0;
+            if (out_rmse) out_rmse[p] = 0.0;
+            if (out_ncorr) out_ncorr[p] = 0;
+            if (out_iters) out_iters[p] = 0;
+        }
+    };
+    Scene *sc = reinterpret_cast<Scene *>(scene);
+    if (!(max_dist > 0.0)) { passthrough(); return VB200_ERR_DISTANCE; }
+    if (estimator != VB200_EST_P2P && (!src_nrm || !sc->has_normals)) { passthrough(); return VB200_ERR_NORMALS; }
+    vb200_batch_t *batch = nullptr;
+    int rc = vb200_batch_create(scene, src_xyz, src_nrm, src_offsets, B, &batch);
+    if (rc != VB200_OK) return rc;
+    rc = vb200_batch_set_problems(batch, nullptr, init_T, B);
+    if (rc == VB200_OK) rc = vb200_batch_run(batch, estimator, gravity_axis, max_dist, rel_fitness, rel_rmse, max_iter);
+    if (rc == VB200_OK) rc = vb200_batch_results(batch, out_T, out_fitness, out_rmse, out_ncorr, out_iters);
+    if (rc == VB200_OK && out_corr) {
+        for (int p = 0; p < B && rc == VB200_OK; p++) {
+            int32_t k = 0;
+            rc = vb200_batch_corr(batch, p, out_corr + 2 * (src_offsets[p] - src_offsets[0]), &k);
+        }
+    }
+    vb200_batch_destroy(batch);
+    return rc;
+}
+
+extern "C" int vb200_register_model_to_scene(vb200_scene_t *scan, const double *model_xyz, const double *model_nrm,
+                                             int64_t m, int level, double threshold, int point_to_plane,
+                                             double out_T[16], int32_t *out_ncorr, int32_t *out_best_level) {
+    if (!scan || !model_xyz || m < 0 || level <= 0 || !out_T) return VB200_ERR_INVALID;
+    const int64_t off[2] = {0, m};
+    vb200_batch_t *batch = nullptr;
+    int rc = vb200_batch_create(scan, model_xyz, model_nrm, off, 1, &batch);
+    if (rc != VB200_OK) return rc;
+    std::vector<double> inits(16 * (size_t)level, 0.0);
+    std::vector<int32_t> ids((size_t)level, 0);
+    const double interval = 2 * M_PI / level;  // src/annotation.cpp:35
+    for (int i = 0; i < level; i++) {
+        double a = interval * i, c = cos(a), s = sin(a);
+        double *T = inits.data() + 16 * (size_t)i;  // AngleAxis(a, UnitY) (src/annotation.cpp:41-43)
+        T[0] = c; T[2] = s; T[5] = 1.0; T[8] = -s; T[10] = c; T[15] = 1.0;
+    }
+    rc = vb200_batch_set_problems(batch, ids.data(), inits.data(), level);
+    // ICPConvergenceCriteria() defaults: 1e-6, 1e-6, 30 (Registration.h:49-50)
+    if (rc == VB200_OK)
+        rc = vb200_batch_run(batch, point_to_plane ? VB200_EST_P2PLANE : VB200_EST_P2P, nullptr, threshold, 1e-6, 1e-6, 30);
+    std::vector<double> Ts(16 * (size_t)level);
+    std::vector<int32_t> nc((size_t)level);
+    if (rc == VB200_OK) rc = vb200_batch_results(batch, Ts.data(), nullptr, nullptr, nc.data(), nullptr);
+    vb200_batch_destroy(batch);
+    if (rc == VB200_ERR_DISTANCE || rc == VB200_ERR_NORMALS) {
+        // every RegistrationICP call returned RegistrationResult(init) with no correspondences, so
+        // best_result stays default-constructed: Identity (src/annotation.cpp:36,59-63)
+        for (int i = 0; i < 16; i++) out_T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+        if (out_ncorr) *out_ncorr = 0;
+        if (out_best_level) *out_best_level = -1;
+        return rc;
+    }
+    if (rc != VB200_OK) return rc;
+    int best = -1, best_k = 0;
+    for (int i = 0; i < level; i++)
+        if (nc[i] > best_k) { best_k = nc[i]; best = i; }  // strict >, first wins (src/annotation.cpp:59)
+    for (int i = 0; i < 16; i++) out_T[i] = best >= 0 ? Ts[16 * (size_t)best + i] : ((i % 5 == 0) ? 1.0 : 0.0);
+    if (out_ncorr) *out_ncorr = best_k;
+    if (out_best_level) *out_best_level = best;
+    return VB200_OK;
+}
+
+extern "C" int vb200_estimate(const double *src_xyz, int64_t m, const double *tgt_xyz, const double *tgt_nrm,
+                              int64_t n, const int32_t *corr, int64_t K, int estimator, const double *gravity_axis,
+                              int device, double out_T[16]) {
+    if (!out_T || K < 0 || (K > 0 && (!src_xyz || !tgt_xyz || !corr))) return VB200_ERR_INVALID;
+    if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY) return VB200_ERR_INVALID;
+    for (int i = 0; i < 16; i++) out_T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    const bool plane = estimator != VB200_EST_P2P;
+    // corres.empty() || !target.HasNormals() -> Identity (TransformationEstimation.cpp:51,79-80)
+    if (K == 0 || (plane && !tgt_nrm)) return VB200_OK;
+    VB_TRY(vb::select_device(device));
+    // marshal the K referenced rows (the reference gathers them too, TransformationEstimation.cpp:52-57)
+    std::vector<double> h((size_t)K * 9);
+    double *vs = h.data(), *vt = vs + 3 * K, *nt = vt + 3 * K;
+    for (int64_t i = 0; i < K; i++) {
+        int64_t a = corr[2 * i], bq = corr[2 * i + 1];
+        if (a < 0 || a >= m || bq < 0 || bq >= n) return VB200_ERR_INVALID;
+        for (int c = 0; c < 3; c++) {
+            vs[3 * i + c] = src_xyz[3 * a + c];
+            vt[3 * i + c] = tgt_xyz[3 * bq + c];
+            nt[3 * i + c] = plane ? tgt_nrm[3 * bq + c] : 0.0;
+        }
+    }
+    vb::SolveParams sp;
+    sp.rel_fitness = sp.rel_rmse = 0.0;
+    sp.max_iter = 0;
+    sp.estimator = estimator;
+    sp.g[0] = 0.0; sp.g[1] = 1.0; sp.g[2] = 0.0;
+    if (estimator == VB200_EST_P2PLANE_GRAVITY && gravity_axis) {
+        double l = sqrt(gravity_axis[0] * gravity_axis[0] + gravity_axis[1] * gravity_axis[1] + gravity_axis[2] * gravity_axis[2]);
+        if (!(l > 0.0)) return VB200_ERR_INVALID;
+        for (int a = 0; a < 3; a++) sp.g[a] = gravity_axis[a] / l;
+    }
+    const int nblk = vb::div_up(K, vb::kChunk);
+    vb::DevBuf<double> d_in, d_part, d_T;
+    VB_CUDA(d_in.alloc((size_t)K * 9));
+    VB_CUDA(d_part.alloc((size_t)nblk * vb::kAcc));
+    VB_CUDA(d_T.alloc(16));
+    VB_CUDA(cudaMemcpy(d_in.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+    if (plane)
+        vb::k_estimate<1><<<nblk, vb::kPassTpb>>>(d_in.p, d_in.p + 3 * K, d_in.p + 6 * K, K, d_part.p);
+    else
+        vb::k_estimate<0><<<nblk, vb::kPassTpb>>>(d_in.p, d_in.p + 3 * K, d_in.p + 6 * K, K, d_part.p);
+    vb::k_estimate_solve<<<1, 256>>>(d_part.p, nblk, d_in.p, sp, d_T.p);
+    VB_CUDA(cudaGetLastError());
+    VB_CUDA(cudaMemcpy(out_T, d_T.p, sizeof(double) * 16, cudaMemcpyDeviceToHost));
+    return VB200_OK;
+}

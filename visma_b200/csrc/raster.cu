@@ -1,0 +1,347 @@
+// raster.cu — vb200_render_depth_batch: a compute-shader-free CUDA z-buffer rasteriser for render_depth.
+// Replaces feh::Renderer::{SetCamera, SetMesh, RenderDepth} (render/renderer.cpp:232-351) and its GLSL
+// vertex shader (render/shaders/basic_mvp.vert:10): the OpenGL context, FBO and synchronous glReadPixels
+// per map become three launches for a whole batch of meshes:
+//   k_clear   z-buffer <- 2^24-1 (glClear depth 1)
+//   k_tris    one thread per (mesh, triangle): float vertex stage, near/far clipping, sub-pixel snapping,
+//             integer edge functions, 24-bit z with atomicMin (GL_LESS); triangles with a large pixel box
+//             are queued instead
+//   k_big     one block per queued triangle
+//   k_resolve uint32 z -> float depth (what glReadPixels(GL_DEPTH_COMPONENT, GL_FLOAT) hands back)
+// The arithmetic is written with explicitly rounded intrinsics (no FMA contraction) and must match the
+// canonical rules restated in oracle/raster_oracle.c bit for bit.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vb {
+
+namespace {
+
+constexpr unsigned kZMax = 16777215u;
+constexpr int kSub = 256;
+constexpr double kClamp = 536870912.0;  // 2^29 sub-pixels
+constexpr int kBigPixels = 1024;        // pixel-box area above which a triangle goes to k_big
+
+struct MeshDesc {
+    float mvp[16];  // column-major (P*V)*M
+    int64_t v_begin, f_begin;
+    int nv, nf;
+};
+
+struct TriSetup {
+    int X0, Y0, X1, Y1, X2, Y2;
+    double z0, z1, z2;
+    int mesh;
+    int pad;
+};
+
+struct ClipV { double x, y, z, w; };
+
+__device__ __forceinline__ int clip_poly(const ClipV *in, int n, ClipV *out, int plane) {
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const ClipV a = in[i], b = in[(i + 1) % n];
+        double da = plane == 0 ? __dadd_rn(a.w, a.z) : __dsub_rn(a.w, a.z);
+        double db = plane == 0 ? __dadd_rn(b.w, b.z) : __dsub_rn(b.w, b.z);
+        bool ia = da >= 0.0, ib = db >= 0.0;
+        if (ia) out[m++] = a;
+        if (ia != ib) {
+            double t = __ddiv_rn(da, __dsub_rn(da, db));
+            ClipV c;
+            c.x = __dadd_rn(a.x, __dmul_rn(t, __dsub_rn(b.x, a.x)));
+            c.y = __dadd_rn(a.y, __dmul_rn(t, __dsub_rn(b.y, a.y)));
+            c.z = __dadd_rn(a.z, __dmul_rn(t, __dsub_rn(b.z, a.z)));
+            c.w = __dadd_rn(a.w, __dmul_rn(t, __dsub_rn(b.w, a.w)));
+            out[m++] = c;
+        }
+    }
+    return m;
+}
+
+__device__ __forceinline__ int snap(double v) {
+    double s = __dmul_rn(v, (double)kSub);
+    if (!(s > -kClamp)) s = -kClamp;
+    if (s > kClamp) s = kClamp;
+    return (int)__double2ll_rn(s);
+}
+
+__device__ __forceinline__ long long floor_div(long long a, long long b) {
+    long long q = a / b, r = a % b;
+    return (r != 0 && r < 0) ? q - 1 : q;
+}
+
+__device__ __forceinline__ bool top_left(long long dx, long long dy) { return dy < 0 || (dy == 0 && dx > 0); }
+
+struct TriRaster {
+    long long X0, Y0, X1, Y1, X2, Y2;
+    long long dx0, dy0, dx1, dy1, dx2, dy2;
+    double z0, z1, z2, a2;
+    bool tl0, tl1, tl2;
+    int i0, i1, j0, j1;
+};
+
+// returns false for degenerate / off-screen triangles
+__device__ __forceinline__ bool tri_prepare(const TriSetup &s, int H, int W, TriRaster &t) {
+    long long X0 = s.X0, Y0 = s.Y0, X1 = s.X1, Y1 = s.Y1, X2 = s.X2, Y2 = s.Y2;
+    double z0 = s.z0, z1 = s.z1, z2 = s.z2;
+    long long area2 = (X1 - X0) * (Y2 - Y0) - (X2 - X0) * (Y1 - Y0);
+    if (area2 == 0) return false;
+    if (area2 < 0) {
+        long long tt;
+        double tz;
+        tt = X1; X1 = X2; X2 = tt;
+        tt = Y1; Y1 = Y2; Y2 = tt;
+        tz = z1; z1 = z2; z2 = tz;
+        area2 = -area2;
+    }
+    long long minX = min(X0, min(X1, X2)), maxX = max(X0, max(X1, X2));
+    long long minY = min(Y0, min(Y1, Y2)), maxY = max(Y0, max(Y1, Y2));
+    long long i0 = floor_div(minX - 128 + (kSub - 1), kSub), i1 = floor_div(maxX - 128, kSub);
+    long long j0 = floor_div(minY - 128 + (kSub - 1), kSub), j1 = floor_div(maxY - 128, kSub);
+    i0 = max(i0, 0ll); j0 = max(j0, 0ll);
+    i1 = min(i1, (long long)W - 1); j1 = min(j1, (long long)H - 1);
+    if (i0 > i1 || j0 > j1) return false;
+    t.X0 = X0; t.Y0 = Y0; t.X1 = X1; t.Y1 = Y1; t.X2 = X2; t.Y2 = Y2;
+    t.dx0 = X2 - X1; t.dy0 = Y2 - Y1; t.dx1 = X0 - X2; t.dy1 = Y0 - Y2; t.dx2 = X1 - X0; t.dy2 = Y1 - Y0;
+    t.tl0 = top_left(t.dx0, t.dy0); t.tl1 = top_left(t.dx1, t.dy1); t.tl2 = top_left(t.dx2, t.dy2);
+    t.z0 = z0; t.z1 = z1; t.z2 = z2;
+    t.a2 = (double)area2;
+    t.i0 = (int)i0; t.i1 = (int)i1; t.j0 = (int)j0; t.j1 = (int)j1;
+    return true;
+}
+
+__device__ __forceinline__ void shade_pixel(const TriRaster &t, int i, int j, long long E0, long long E1,
+                                            long long E2, unsigned *zbuf, int W) {
+    if (!(E0 > 0 || (E0 == 0 && t.tl0))) return;
+    if (!(E1 > 0 || (E1 == 0 && t.tl1))) return;
+    if (!(E2 > 0 || (E2 == 0 && t.tl2))) return;
+    double num = __dadd_rn(__dadd_rn(__dmul_rn((double)E0, t.z0), __dmul_rn((double)E1, t.z1)),
+                           __dmul_rn((double)E2, t.z2));
+    double z = __ddiv_rn(num, t.a2);
+    double qd = __dmul_rn(z, (double)kZMax);
+    long long q = __double2ll_rn(qd);
+    if (!(qd > 0.0)) q = 0;
+    if (q > (long long)kZMax) q = kZMax;
+    atomicMin(zbuf + (size_t)j * W + i, (unsigned)q);  // GL_LESS against the stored minimum
+}
+
+__device__ __forceinline__ void edge_at(const TriRaster &t, long long px, long long py, long long &E0,
+                                        long long &E1, long long &E2) {
+    E0 = t.dx0 * (py - t.Y1) - t.dy0 * (px - t.X1);
+    E1 = t.dx1 * (py - t.Y2) - t.dy1 * (px - t.X2);
+    E2 = t.dx2 * (py - t.Y0) - t.dy2 * (px - t.X0);
+}
+
+__global__ void __launch_bounds__(256) k_clear(unsigned *__restrict__ z, int64_t n) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        *reinterpret_cast<uint4 *>(z + i) = make_uint4(kZMax, kZMax, kZMax, kZMax);
+    } else {
+        for (; i < n; i++) z[i] = kZMax;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_tris(const MeshDesc *__restrict__ meshes, const int *__restrict__ tri_mesh_start,
+                                              int n_mesh, int64_t n_tri_total, const float *__restrict__ V,
+                                              const int *__restrict__ F, int H, int W, unsigned *__restrict__ zbuf,
+                                              TriSetup *__restrict__ big, int *__restrict__ big_count) {
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_tri_total) return;
+    // which mesh does this triangle belong to: binary search over the per-mesh triangle offsets
+    int lo = 0, hi = n_mesh;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (tri_mesh_start[mid] <= gid) lo = mid; else hi = mid;
+    }
+    const int mesh = lo;
+    const MeshDesc &md = meshes[mesh];
+    const int f = (int)(gid - tri_mesh_start[mesh]);
+    const int *tri = F + 3 * (md.f_begin + f);
+    ClipV poly[8], tmp[8];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int vi = tri[k];
+        if (vi < 0 || vi >= md.nv) return;
+        const float *p = V + 3 * (md.v_begin + vi);
+        const float x = p[0], y = p[1], z = p[2];
+        float c[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            float s = __fmul_rn(md.mvp[0 * 4 + r], x);
+            s = __fadd_rn(s, __fmul_rn(md.mvp[1 * 4 + r], y));
+            s = __fadd_rn(s, __fmul_rn(md.mvp[2 * 4 + r], z));
+            s = __fadd_rn(s, md.mvp[3 * 4 + r]);
+            c[r] = s;
+        }
+        poly[k].x = c[0]; poly[k].y = c[1]; poly[k].z = c[2]; poly[k].w = c[3];
+    }
+    int n = clip_poly(poly, 3, tmp, 0);
+    if (n < 3) return;
+    n = clip_poly(tmp, n, poly, 1);
+    if (n < 3) return;
+    int X[8], Y[8];
+    double Z[8];
+    for (int k = 0; k < n; k++) {
+        double iw = __ddiv_rn(1.0, poly[k].w);
+        double xn = __dmul_rn(poly[k].x, iw), yn = __dmul_rn(poly[k].y, iw), zn = __dmul_rn(poly[k].z, iw);
+        X[k] = snap(__dmul_rn(__dadd_rn(xn, 1.0), __dmul_rn((double)W, 0.5)));
+        Y[k] = snap(__dmul_rn(__dadd_rn(yn, 1.0), __dmul_rn((double)H, 0.5)));
+        Z[k] = __dmul_rn(__dadd_rn(zn, 1.0), 0.5);
+    }
+    unsigned *zb = zbuf + (size_t)mesh * H * W;
+    for (int k = 1; k + 1 < n; k++) {
+        TriSetup s;
+        s.X0 = X[0]; s.Y0 = Y[0]; s.z0 = Z[0];
+        s.X1 = X[k]; s.Y1 = Y[k]; s.z1 = Z[k];
+        s.X2 = X[k + 1]; s.Y2 = Y[k + 1]; s.z2 = Z[k + 1];
+        s.mesh = mesh; s.pad = 0;
+        TriRaster t;
+        if (!tri_prepare(s, H, W, t)) continue;
+        if ((int64_t)(t.i1 - t.i0 + 1) * (t.j1 - t.j0 + 1) > kBigPixels) {
+            big[atomicAdd(big_count, 1)] = s;
+            continue;
+        }
+        for (int j = t.j0; j <= t.j1; j++) {
+            long long py = (long long)j * kSub + 128, px = (long long)t.i0 * kSub + 128;
+            long long E0, E1, E2;
+            edge_at(t, px, py, E0, E1, E2);
+            for (int i = t.i0; i <= t.i1; i++) {
+                shade_pixel(t, i, j, E0, E1, E2, zb, W);
+                E0 -= t.dy0 * kSub; E1 -= t.dy1 * kSub; E2 -= t.dy2 * kSub;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_big(const TriSetup *__restrict__ big, const int *__restrict__ big_count,
+                                             int H, int W, unsigned *__restrict__ zbuf) {
+    const int count = *big_count;
+    for (int q = blockIdx.x; q < count; q += gridDim.x) {
+        TriRaster t;
+        const TriSetup s = big[q];
+        if (!tri_prepare(s, H, W, t)) continue;
+        unsigned *zb = zbuf + (size_t)s.mesh * H * W;
+        const int bw = t.i1 - t.i0 + 1, bh = t.j1 - t.j0 + 1;
+        for (int p = threadIdx.x; p < bw * bh; p += blockDim.x) {
+            int i = t.i0 + p % bw, j = t.j0 + p / bw;
+            long long E0, E1, E2;
+            edge_at(t, (long long)i * kSub + 128, (long long)j * kSub + 128, E0, E1, E2);
+            shade_pixel(t, i, j, E0, E1, E2, zb, W);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_resolve(const unsigned *__restrict__ z, float *__restrict__ depth, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) depth[i] = (float)__ddiv_rn((double)z[i], (double)kZMax);
+}
+
+// ---- host-side camera maths (float, evaluated in the order the reference / glm evaluate it) ---------
+// Renderer::SetCamera(zn, zf, intrinsics): frustum extents with top/bottom flipped (render/renderer.cpp:259-267)
+// fed to glm::frustum (RH, z in [-1,1]).
+void projection_matrix(float zn, float zf, float fx, float fy, float cx, float cy, int H, int W, float P[16]) {
+    volatile float left = -cx / fx * zn;
+    volatile float right = (float)(((double)(float)W - 1.0 - (double)cx) / (double)fx * (double)zn);
+    volatile float bottom = cy / fy * zn;
+    volatile float top = (cy - (float)(H - 1)) / fy * zn;
+    for (int i = 0; i < 16; i++) P[i] = 0.0f;
+    P[0] = (2.0f * zn) / (right - left);
+    P[5] = (2.0f * zn) / (top - bottom);
+    P[8] = (right + left) / (right - left);
+    P[9] = (top + bottom) / (top - bottom);
+    P[10] = -(zf + zn) / (zf - zn);
+    P[11] = -1.0f;
+    P[14] = -(2.0f * zf * zn) / (zf - zn);
+}
+
+void mat4f_mul(const float a[16], const float b[16], float c[16]) {  // column-major, left-to-right sums
+    float r[16];
+    for (int col = 0; col < 4; col++)
+        for (int row = 0; row < 4; row++) {
+            volatile float s = a[0 * 4 + row] * b[col * 4 + 0];
+            s = s + a[1 * 4 + row] * b[col * 4 + 1];
+            s = s + a[2 * 4 + row] * b[col * 4 + 2];
+            s = s + a[3 * 4 + row] * b[col * 4 + 3];
+            r[col * 4 + row] = s;
+        }
+    memcpy(c, r, sizeof(r));
+}
+
+}  // namespace
+
+}  // namespace vb
+
+extern "C" int vb200_render_depth_batch(const float *V_concat, const int64_t *v_off, const int32_t *F_concat,
+                                        const int64_t *f_off, int32_t n_mesh, const float *model_T,
+                                        const float view_T[16], float zn, float zf, float fx, float fy, float cx,
+                                        float cy, int H, int W, int device, uint32_t *out_z24, float *out_depth) {
+    using namespace vb;
+    if (n_mesh < 0 || H <= 0 || W <= 0 || !v_off || !f_off || !view_T || (n_mesh > 0 && !model_T))
+        return VB200_ERR_INVALID;
+    if (n_mesh == 0) return VB200_OK;
+    const int64_t nv = v_off[n_mesh] - v_off[0], nf = f_off[n_mesh] - f_off[0];
+    if (nv < 0 || nf < 0 || (nv > 0 && !V_concat) || (nf > 0 && !F_concat)) return VB200_ERR_INVALID;
+    VB_TRY(select_device(device));
+    // camera: projection (SetCamera(zn,zf,...)) and view = diag(1,-1,-1,1) * pose (SetCamera(pose),
+    // render/renderer.cpp:284-300); MVP = (P*V)*M as the vertex shader's left-to-right product
+    float P[16], Vw[16], PV[16];
+    projection_matrix(zn, zf, fx, fy, cx, cy, H, W, P);
+    const float v2g[16] = {1, 0, 0, 0, 0, -1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1};
+    mat4f_mul(v2g, view_T, Vw);
+    mat4f_mul(P, Vw, PV);
+    std::vector<MeshDesc> meshes((size_t)n_mesh);
+    std::vector<int> tri_start((size_t)n_mesh + 1);
+    for (int m = 0; m < n_mesh; m++) {
+        MeshDesc &d = meshes[m];
+        mat4f_mul(PV, model_T + 16 * (size_t)m, d.mvp);
+        d.v_begin = v_off[m] - v_off[0];
+        d.f_begin = f_off[m] - f_off[0];
+        int64_t mv = v_off[m + 1] - v_off[m], mf = f_off[m + 1] - f_off[m];
+        if (mv < 0 || mf < 0 || mv > 0x7fffffff || f_off[m + 1] - f_off[0] > 0x7fffffff) return VB200_ERR_INVALID;
+        d.nv = (int)mv;
+        d.nf = (int)mf;
+        tri_start[m] = (int)d.f_begin;
+    }
+    tri_start[n_mesh] = (int)nf;
+
+    cudaStream_t st;
+    VB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
+    const int64_t npix = (int64_t)n_mesh * H * W;
+    DevBuf<float> d_V, d_depth;
+    DevBuf<int> d_F, d_tri_start, d_big_count;
+    DevBuf<MeshDesc> d_mesh;
+    DevBuf<unsigned> d_z;
+    DevBuf<TriSetup> d_big;
+    VB_CUDA(d_V.alloc(3 * (size_t)std::max<int64_t>(nv, 1)));
+    VB_CUDA(d_F.alloc(3 * (size_t)std::max<int64_t>(nf, 1)));
+    VB_CUDA(d_mesh.alloc((size_t)n_mesh));
+    VB_CUDA(d_tri_start.alloc((size_t)n_mesh + 1));
+    VB_CUDA(d_z.alloc((size_t)npix));
+    VB_CUDA(d_big.alloc(3 * (size_t)std::max<int64_t>(nf, 1)));
+    VB_CUDA(d_big_count.alloc(1));
+    if (nv) VB_CUDA(cudaMemcpyAsync(d_V.p, V_concat + 3 * v_off[0], sizeof(float) * 3 * (size_t)nv, cudaMemcpyHostToDevice, st));
+    if (nf) VB_CUDA(cudaMemcpyAsync(d_F.p, F_concat + 3 * f_off[0], sizeof(int) * 3 * (size_t)nf, cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMemcpyAsync(d_mesh.p, meshes.data(), sizeof(MeshDesc) * (size_t)n_mesh, cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMemcpyAsync(d_tri_start.p, tri_start.data(), sizeof(int) * ((size_t)n_mesh + 1), cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMemsetAsync(d_big_count.p, 0, sizeof(int), st));
+    k_clear<<<div_up(div_up(npix, 4), 256), 256, 0, st>>>(d_z.p, npix);
+    if (nf) {
+        k_tris<<<div_up(nf, 128), 128, 0, st>>>(d_mesh.p, d_tri_start.p, n_mesh, nf, d_V.p, d_F.p, H, W, d_z.p, d_big.p, d_big_count.p);
+        k_big<<<kNumSMsB200 * 4, 256, 0, st>>>(d_big.p, d_big_count.p, H, W, d_z.p);
+    }
+    VB_CUDA(cudaGetLastError());
+    if (out_depth) {
+        VB_CUDA(d_depth.alloc((size_t)npix));
+        k_resolve<<<div_up(npix, 256), 256, 0, st>>>(d_z.p, d_depth.p, npix);
+        VB_CUDA(cudaGetLastError());
+        VB_CUDA(cudaMemcpyAsync(out_depth, d_depth.p, sizeof(float) * (size_t)npix, cudaMemcpyDeviceToHost, st));
+    }
+    if (out_z24) VB_CUDA(cudaMemcpyAsync(out_z24, d_z.p, sizeof(unsigned) * (size_t)npix, cudaMemcpyDeviceToHost, st));
+    VB_CUDA(cudaStreamSynchronize(st));
+    return VB200_OK;
+}

@@ -1,0 +1,96 @@
+"""Python mirror of feh::Renderer's depth interface (render/renderer.h:41-118) over the C ABI.
+
+Same method names and argument meaning as the reference class; no OpenGL / GLFW / glog / OpenCV.  Matrices
+are column-major float32[16] exactly as the reference passes Eigen ColMajor matrices to glUniformMatrix4fv.
+The production host side is the C++ class in visma_b200/host/renderer_b200.h.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib
+
+
+def LinearizeDepth(zb, z_near, z_far):
+    """render/renderer.h:32-36"""
+    return 2 * z_near * z_far / (z_far + z_near - (2 * zb - 1) * (z_far - z_near))
+
+
+class Renderer:
+    def __init__(self, maxHeight, maxWidth, major_version=3, minor_version=2, device=0):
+        # major/minor are the reference's OpenGL context version (renderer.cpp:48): accepted and ignored
+        self.rows_, self.cols_ = int(maxHeight), int(maxWidth)
+        self.device = device
+        self.fx_ = self.fy_ = self.cx_ = self.cy_ = 0.0
+        self.z_near_, self.z_far_ = 0.05, 10.0
+        self.pose_ = np.eye(4, dtype=np.float32).T.reshape(-1).copy()
+        self.V_ = np.zeros((0, 3), np.float32)
+        self.F_ = np.zeros((0, 3), np.int32)
+
+    def SetCamera(self, *args):
+        """SetCamera(z_near, z_far, fx, fy, cx, cy) | SetCamera(z_near, z_far, intrinsics[4]) |
+        SetCamera(pose 4x4, initial-camera -> current-camera)  (render/renderer.cpp:232-300)"""
+        if len(args) == 6:
+            self.z_near_, self.z_far_, self.fx_, self.fy_, self.cx_, self.cy_ = [float(a) for a in args]
+        elif len(args) == 3:
+            self.z_near_, self.z_far_ = float(args[0]), float(args[1])
+            self.fx_, self.fy_, self.cx_, self.cy_ = [float(a) for a in args[2]]
+        elif len(args) == 1:
+            self.pose_ = np.asarray(args[0], np.float32).reshape(4, 4).T.reshape(-1).copy()  # to column-major
+        else:
+            raise TypeError("SetCamera: bad arguments")
+
+    def SetMesh(self, vertices, faces):
+        """SetMesh(V n x 3 float, F m x 3 int)  (render/renderer.cpp:303-319)"""
+        self.V_ = np.ascontiguousarray(np.asarray(vertices, np.float32).reshape(-1, 3))
+        self.F_ = np.ascontiguousarray(np.asarray(faces, np.int32).reshape(-1, 3))
+
+    def RenderDepth(self, model, out=None):
+        """RenderDepth(model 4x4) -> H x W float32 window depth in [0,1], 1 = background, row 0 = image top
+        (render/renderer.cpp:321-351).  `out`, when given, must be H x W float32 (the reference CHECKs)."""
+        d = self.RenderDepthBatch([model])[0]
+        if out is not None:
+            if out.shape != (self.rows_, self.cols_) or out.dtype != np.float32:
+                raise ValueError("depth_map must be %dx%d float32" % (self.rows_, self.cols_))
+            out[...] = d
+            return out
+        return d
+
+    def RenderDepthBatch(self, models, meshes=None, want_z24=False):
+        """Batch form: one depth map per model pose.  meshes = optional list of (V, F), one per pose;
+        default = the mesh set with SetMesh for every pose."""
+        n = len(models)
+        if meshes is None:
+            meshes = [(self.V_, self.F_)] * n
+        Vs = [np.ascontiguousarray(np.asarray(v, np.float32).reshape(-1, 3)) for v, _ in meshes]
+        Fs = [np.ascontiguousarray(np.asarray(f, np.int32).reshape(-1, 3)) for _, f in meshes]
+        v_off = np.zeros(n + 1, np.int64); v_off[1:] = np.cumsum([len(v) for v in Vs])
+        f_off = np.zeros(n + 1, np.int64); f_off[1:] = np.cumsum([len(f) for f in Fs])
+        V = np.ascontiguousarray(np.concatenate(Vs)) if n else np.zeros((0, 3), np.float32)
+        F = np.ascontiguousarray(np.concatenate(Fs)) if n else np.zeros((0, 3), np.int32)
+        M = np.ascontiguousarray(np.stack([np.asarray(m, np.float32).reshape(4, 4).T.reshape(-1) for m in models])) \
+            if n else np.zeros((0, 16), np.float32)
+        H, W = self.rows_, self.cols_
+        depth = np.empty((n, H, W), np.float32)
+        z24 = np.empty((n, H, W), np.uint32) if want_z24 else None
+        fp = C.POINTER(C.c_float)
+        check(lib().vb200_render_depth_batch(
+            V.ctypes.data_as(fp), v_off.ctypes.data_as(C.POINTER(C.c_int64)),
+            F.ctypes.data_as(C.POINTER(C.c_int32)), f_off.ctypes.data_as(C.POINTER(C.c_int64)), n,
+            M.ctypes.data_as(fp), self.pose_.ctypes.data_as(fp), self.z_near_, self.z_far_, self.fx_, self.fy_,
+            self.cx_, self.cy_, H, W, self.device,
+            None if z24 is None else z24.ctypes.data_as(C.POINTER(C.c_uint32)), depth.ctypes.data_as(fp)),
+            "vb200_render_depth_batch")
+        return (depth, z24) if want_z24 else depth
+
+    # accessors (render/renderer.h:96-109)
+    def fx(self): return self.fx_
+    def fy(self): return self.fy_
+    def cx(self): return self.cx_
+    def cy(self): return self.cy_
+    def z_near(self): return self.z_near_
+    def z_far(self): return self.z_far_
+    def width(self): return self.cols_
+    def cols(self): return self.cols_
+    def height(self): return self.rows_
+    def rows(self): return self.rows_
