@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — ICP iterations/s on the BASELINE workload (2 M-point scene x 32 objects x 50 k points).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (B200, CUDA)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (Open3D/FLANN/Eigen)
+
+A "step" is one ICP iteration — correspondence pass + estimator update (Registration.cpp:172-178) — for all
+32 objects of a rank.  Under torchrun every rank holds the whole scene and its own 32 objects (objects shard
+with no data-path collective; one all-gather of the final poses), so per-GPU work is fixed: weak scaling.
+
+  value   device-resident: sources and scene already in HBM, K single-iteration steps timed with CUDA events
+          on the library's stream, L2 flushed (untimed) before every step, max over ranks.
+  e2e     the public C-ABI call vb200_icp_run with HOST buffers (pinned): H2D of the 32 sources, the spatial
+          sort, 30 iterations, D2H of the poses, every call; iterations/s = 30 / call time.
+  roofline  k_pass (the correspondence + reduction kernel): SURVEY §8d algorithmic bytes / its measured time.
+  cpu_baseline  the unmodified reference (oracle/_ref) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SCENE, N_OBJ, M_PTS, MAX_DIST, ICP_ITERS = 2_000_000, 32, 50_000, 0.075, 30
+METRIC = "icp_iterations_per_s_2Mpt_scene_x32_objects"
+UNIT = "iterations/s"
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def algorithmic_bytes(n_scene, m_total, k_total, n_obj):
+    """16N [scene once] + sum(16 M + 8 M) [source in, corr out] + sum K (8 + 16 + 16 + 16)
+    [corr in, src, target point, target normal] + 27*8 per object [JTJ/JTr out]."""
+    return 16 * n_scene + 24 * m_total + 56 * k_total + 216 * n_obj
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.p = gpu, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(rank):
+    from visma_b200 import synth
+    return synth.make_room_scene(N_SCENE, N_OBJ, M_PTS, source_seed=rank)
+
+
+# ------------------------------------------------------------------------------------------------ reference
+def reference_sample(d, n_obj_sample, estimator_p2plane=True):
+    """One bounded sample of the workload on the reference's own CPU path: RegistrationICP (tree build
+    included, as the reference rebuilds it per call) for n_obj_sample of the 32 objects, 30 iterations each
+    with the convergence test disabled so both arms do identical work.  Returns seconds."""
+    from oracle import pyref
+    t0 = time.perf_counter()
+    for b in range(n_obj_sample):
+        src, sn = d["sources"][b]
+        pyref.registration_icp(src, d["scene_xyz"], MAX_DIST, d["T_init"][b],
+                               pyref.P2PLANE if estimator_p2plane else pyref.P2P, src_nrm=sn,
+                               tgt_nrm=d["scene_nrm"], rel_fitness=0.0, rel_rmse=0.0, max_iter=ICP_ITERS)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return  # the CPU baseline runs once, on rank 0's host cores
+    from oracle import pyref
+    if not pyref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvisma_ref.so not built"}))
+        return
+    cores = pyref.num_threads()
+    d = make_workload(0)
+    n_s = 1
+    for _ in range(args.warmup):
+        reference_sample(d, n_s)
+    ts = [reference_sample(d, n_s) for _ in range(args.steps)]
+    t = float(np.mean(ts))
+    # one sample = ICP_ITERS iterations of n_s objects; a full iteration covers N_OBJ objects
+    value = ICP_ITERS / (t * N_OBJ / n_s)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "2M-pt synthetic room scene x 32 chair fragments x 50k pts, point-to-plane, "
+                                   "max_dist 0.075, 30 iterations/object (convergence test off)",
+                       "n_scene": N_SCENE, "objects": N_OBJ, "pts_per_object": M_PTS,
+                       "reference": "open3d::RegistrationICP (Open3D 0.3.0 + FLANN 1.8.4 + Eigen 3.3.2, "
+                                    "-O3 -fopenmp), KD-tree rebuilt per call as in Registration.cpp:160-161"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": "%d of 32 objects per step, x%d steps, scaled to 32" % (n_s, args.steps)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from visma_b200 import registration as reg
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    d = make_workload(rank)
+    est = reg.TransformationEstimationPointToPlane()
+    t0 = time.perf_counter()
+    scene = reg.Scene(reg.PointCloud(d["scene_xyz"], d["scene_nrm"]), MAX_DIST, device=local)
+    scene_build_s = time.perf_counter() - t0
+    clouds = [reg.PointCloud(p, n) for p, n in d["sources"]]
+    batch = reg.Batch(scene, clouds)
+    stream = torch.cuda.ExternalStream(scene.stream(), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(timed):
+        flush.fill_(rank + 1)           # untimed: evict L2 between timed iterations
+        torch.cuda.synchronize()
+        batch.iterate(est, MAX_DIST, 1)  # k_pass + k_solve, recorded by the library's own events
+        p_ms, s_ms = batch.last_kernel_ms()
+        return p_ms, s_ms
+
+    # ---- device-resident leg ("value")
+    batch.set_problems(d["T_init"])
+    for _ in range(args.warmup):
+        one_step(False)
+    batch.set_problems(d["T_init"])      # timed steps replay the real trajectory from the initial poses
+    launches0 = batch.launches()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    pass_ms, solve_ms = [], []
+    for _ in range(args.steps):
+        p_ms, s_ms = one_step(True)
+        pass_ms.append(p_ms)
+        solve_ms.append(s_ms)
+    # the single collective of the path: all-gather of the final poses
+    res = batch.results()
+    poses = torch.tensor(np.stack([r.transformation_ for r in res]), device=dev)
+    ag_ms = 0.0
+    if world > 1:
+        out = [torch.empty_like(poses) for _ in range(world)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather(out, poses)
+        e1.record()
+        torch.cuda.synchronize()
+        ag_ms = e0.elapsed_time(e1)
+    barrier()
+    launches = batch.launches() - launches0
+    total_ms = float(np.sum(pass_ms) + np.sum(solve_ms)) + ag_ms
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * args.steps / (total_ms * 1e-3)
+
+    # the real loop, back to back without flushes (informational: what one RegistrationICP run costs)
+    batch.set_problems(d["T_init"])
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        batch.iterate(est, MAX_DIST, ICP_ITERS)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    loop_ms = e0.elapsed_time(e1) / ICP_ITERS
+
+    # ---- end-to-end leg: the C-ABI call with pinned host buffers, copies inside the timed region
+    src_all = torch.from_numpy(np.concatenate([c.points_ for c in clouds])).pin_memory()
+    pinned = [reg.PointCloud(src_all.numpy()[i * M_PTS:(i + 1) * M_PTS], src_all.numpy()[i * M_PTS:(i + 1) * M_PTS])
+              for i in range(N_OBJ)]
+    crit = reg.ICPConvergenceCriteria(0.0, 0.0, ICP_ITERS)  # never "converged": exactly 30 iterations
+    n_e2e = max(3, min(args.steps, 10))
+    reg.RegistrationICPBatch(pinned, scene, MAX_DIST, d["T_init"], est, crit, want_corr=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        r_e2e = reg.RegistrationICPBatch(pinned, scene, MAX_DIST, d["T_init"], est, crit, want_corr=False)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * ICP_ITERS / float(te.item())
+    clocks = sampler.stop()
+
+    # sanity: the timed work converged to the ground truth (guards against timing a no-op)
+    from visma_b200 import synth
+    errs = np.array([synth.pose_error(r.transformation_, T) for r, T in zip(r_e2e, d["T_gt"])])
+    k_total = int(sum(len(r.correspondence_set_) for r in r_e2e))
+    ok = bool((errs[:, 0] < 5e-3).all() and (errs[:, 1] < 5e-3).all())
+
+    if rank == 0:
+        peak, how = measured_peak()
+        b_alg = algorithmic_bytes(N_SCENE, N_OBJ * M_PTS, k_total, N_OBJ)
+        p_ms = float(np.mean(pass_ms))
+        achieved = b_alg / (p_ms * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                from oracle import pyref
+                if pyref.available():
+                    ts = reference_sample(d, 1)
+                    v = ICP_ITERS / (ts * N_OBJ)
+                    cpu = {"value": v, "unit": UNIT, "cores": pyref.num_threads(), "kind": "reference",
+                           "sample": "open3d::RegistrationICP (tree build + 30 point-to-plane iterations) on 1 of "
+                                     "the 32 objects, scaled to 32; %.1f s of CPU time" % ts}
+                else:
+                    from oracle import pyoracle
+                    t1 = time.perf_counter()
+                    ix = pyoracle.Index(d["scene_xyz"], MAX_DIST)
+                    ix.registration_icp(d["sources"][0][0], MAX_DIST, d["T_init"][0], pyoracle.P2PLANE,
+                                        src_nrm=d["sources"][0][1], tgt_nrm=d["scene_nrm"], rel_fitness=0.0,
+                                        rel_rmse=0.0, max_iter=ICP_ITERS)
+                    ts = time.perf_counter() - t1
+                    cpu = {"value": ICP_ITERS / (ts * N_OBJ), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                           "sample": "oracle restatement, 1 of 32 objects scaled to 32; %.1f s" % ts}
+            except Exception as ex:  # the baseline is informational; never lose the GPU line over it
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %s" % ex}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "2M-pt synthetic room scene x 32 chair fragments x 50k pts per GPU, "
+                                   "point-to-plane, max_dist 0.075; step = 1 ICP iteration of all 32 objects "
+                                   "(k_pass + k_solve)",
+                       "n_scene": N_SCENE, "objects_per_gpu": N_OBJ, "pts_per_object": M_PTS,
+                       "l2": "256 MiB flush before every timed step (untimed)",
+                       "back_to_back_ms_per_iteration_no_flush": loop_ms,
+                       "pass_ms": p_ms, "solve_ms": float(np.mean(solve_ms)), "allgather_ms": ag_ms,
+                       "scene_build_s": scene_build_s, "converged_to_ground_truth": ok,
+                       "max_pose_err_rad_m": [float(errs[:, 0].max()), float(errs[:, 1].max())]},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(src_all.numel() * 8 + N_OBJ * 16 * 8 + (N_OBJ + 1) * 8),
+                    "d2h_bytes_per_step": int(N_OBJ * (16 * 8 + 8 + 8 + 4 + 4)),
+                    "note": "one vb200_icp_run call = upload + sort + 30 iterations + results; %.2f ms/call" % (e2e_s * 1e3)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_pass<point-to-plane>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how,
+                         "algorithmic_bytes": b_alg},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 30 and "--steps" not in " ".join(sys.argv):
+            args.steps = 2
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -111,6 +111,14 @@ int vb200_batch_results(vb200_batch_t *batch, double *out_T, double *out_fitness
 int vb200_batch_corr(vb200_batch_t *batch, int32_t p, int32_t *out_corr, int32_t *out_k);
 /* number of kernel launches issued by this batch since creation (bench.py's gpu_launches) */
 int64_t vb200_batch_launches(const vb200_batch_t *batch);
+/* n_iter unconditional ICP iterations (correspondence pass + estimator update, Registration.cpp:172-178)
+ * continuing from the problems' current transforms, with no convergence test: the unit bench.py times.
+ * Asynchronous on the scene's stream. */
+int vb200_batch_iterate(vb200_batch_t *batch, int estimator, const double *gravity_axis, double max_dist,
+                        int n_iter);
+/* device time (ms, CUDA events on the scene's stream) of the correspondence-pass kernel launches and of
+ * the solve kernel launches issued by the most recent vb200_batch_iterate call; synchronises. */
+int vb200_batch_last_kernel_ms(vb200_batch_t *batch, float *pass_ms, float *solve_ms);
 
 /* ---- estimator plug-in: replaces TransformationEstimation::ComputeTransformation(source, target,
  * corres) (O3D/src/Core/Registration/TransformationEstimation.h:51-66; VISMA's subclass

@@ -62,7 +62,8 @@ def test_icp_batch_matches_oracle(vb, oracle, scene, name):
         assert abs(r.iterations_ - o["iters"]) <= 1
         # converged pose is near the ground truth the scene was built from
         grot, gtr = vb.synth.pose_error(r.transformation_, scene["T_gt"][b])
-        if name != "p2p" and name != "cicp":
+        # (the 4-DoF estimator cannot undo the +-1 degree roll/pitch of T_init: it has its own test below)
+        if name == "p2plane":
             assert grot < 5e-3 and gtr < 5e-3, (name, b, grot, gtr)
 
 

@@ -436,6 +436,9 @@ struct Batch {
     double *d_partials = nullptr;
     int *d_corr = nullptr;
     int64_t launches = 0;
+    int iter_base = 0;                       // running pass index for vb200_batch_iterate
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // pass start / pass end = solve start / solve end
+    bool ev_valid = false;
 };
 
 static void batch_free_problems(Batch *b) {
@@ -447,6 +450,8 @@ static void batch_free_problems(Batch *b) {
 static void batch_free(Batch *b) {
     if (!b) return;
     batch_free_problems(b);
+    for (int i = 0; i < 3; i++)
+        if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     cudaFree(b->d_src); cudaFree(b->d_src_orig); cudaFree(b->d_cloud_off);
     delete b;
 }
@@ -496,6 +501,7 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
     cudaStream_t st = b->scene->stream;
     batch_free_problems(b);
     b->P = P;
+    b->iter_base = 0;
     b->probs.resize((size_t)P);
     std::vector<BlockTask> tasks;
     std::vector<ProbState> states((size_t)P);
@@ -582,11 +588,75 @@ static int batch_run(Batch *b, int estimator, const double *gravity, double max_
     return VB200_OK;
 }
 
+// n unconditional iterations from the current transforms (no convergence test, `done` never set)
+static int batch_iterate(Batch *b, int estimator, const double *gravity, double max_dist, int n_iter) {
+    Scene *sc = b->scene;
+    cudaStream_t st = sc->stream;
+    if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY || n_iter < 0) return VB200_ERR_INVALID;
+    if (!(max_dist > 0.0)) return VB200_ERR_DISTANCE;
+    if (max_dist > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
+    const bool plane = estimator != VB200_EST_P2P;
+    if (plane && (!b->has_normals || !sc->has_normals)) return VB200_ERR_NORMALS;
+    if (b->P == 0 || b->nblk == 0) return VB200_OK;
+    PassParams pp;
+    pp.r2 = (double)(float)(max_dist * max_dist);
+    pp.r2_ub = r2_upper_bound(sc->grid.p, pp.r2);
+    SolveParams sp;
+    sp.rel_fitness = sp.rel_rmse = -1.0;  // |delta| < -1 never holds: no convergence exit
+    sp.max_iter = 0x7fffffff;
+    sp.estimator = estimator;
+    sp.g[0] = 0.0; sp.g[1] = 1.0; sp.g[2] = 0.0;
+    if (estimator == VB200_EST_P2PLANE_GRAVITY && gravity) {
+        double l = sqrt(gravity[0] * gravity[0] + gravity[1] * gravity[1] + gravity[2] * gravity[2]);
+        if (!(l > 0.0)) return VB200_ERR_INVALID;
+        for (int a = 0; a < 3; a++) sp.g[a] = gravity[a] / l;
+    }
+    for (int i = 0; i < 3; i++)
+        if (!b->ev[i]) VB_CUDA(cudaEventCreate(&b->ev[i]));
+    const bool timed = n_iter == 1;  // per-kernel events only make sense around a single iteration
+    for (int it = 0; it < n_iter; it++) {
+        if (timed) VB_CUDA(cudaEventRecord(b->ev[0], st));
+        if (plane)
+            k_pass<1><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
+        else
+            k_pass<0><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
+        if (timed) VB_CUDA(cudaEventRecord(b->ev[1], st));
+        k_solve<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, sp, b->iter_base++);
+        if (timed) VB_CUDA(cudaEventRecord(b->ev[2], st));
+        b->launches += 2;
+    }
+    b->ev_valid = timed;
+    VB_CUDA(cudaGetLastError());
+    return VB200_OK;
+}
+
 }  // namespace vb
 
 // ======================================================================================================
 using vb::Batch;
 using vb::Scene;
+
+extern "C" int vb200_batch_iterate(vb200_batch_t *batch, int estimator, const double *gravity_axis,
+                                   double max_dist, int n_iter) {
+    if (!batch) return VB200_ERR_INVALID;
+    Batch *b = reinterpret_cast<Batch *>(batch);
+    VB_CUDA(cudaSetDevice(b->scene->device));
+    return vb::batch_iterate(b, estimator, gravity_axis, max_dist, n_iter);
+}
+
+extern "C" int vb200_batch_last_kernel_ms(vb200_batch_t *batch, float *pass_ms, float *solve_ms) {
+    if (!batch) return VB200_ERR_INVALID;
+    Batch *b = reinterpret_cast<Batch *>(batch);
+    if (!b->ev_valid) return VB200_ERR_INVALID;
+    VB_CUDA(cudaSetDevice(b->scene->device));
+    VB_CUDA(cudaEventSynchronize(b->ev[2]));
+    float a = 0.f, c = 0.f;
+    VB_CUDA(cudaEventElapsedTime(&a, b->ev[0], b->ev[1]));
+    VB_CUDA(cudaEventElapsedTime(&c, b->ev[1], b->ev[2]));
+    if (pass_ms) *pass_ms = a;
+    if (solve_ms) *solve_ms = c;
+    return VB200_OK;
+}
 
 extern "C" int vb200_batch_create(vb200_scene_t *scene, const double *src_xyz, const double *src_nrm,
                                   const int64_t *src_offsets, int32_t n_clouds, vb200_batch_t **out) {

@@ -209,6 +209,18 @@ class Batch:
     def launches(self):
         return int(lib().vb200_batch_launches(self._h))
 
+    def iterate(self, estimation, max_dist, n_iter=1):
+        """n unconditional ICP iterations from the current transforms (no convergence test); async."""
+        g = getattr(estimation, "gravity_axis", None)
+        g = _f64(g) if g is not None else None
+        check(lib().vb200_batch_iterate(self._h, estimation.kind, _dp(g), float(max_dist), int(n_iter)),
+              "vb200_batch_iterate")
+
+    def last_kernel_ms(self):
+        a, b = C.c_float(), C.c_float()
+        check(lib().vb200_batch_last_kernel_ms(self._h, C.byref(a), C.byref(b)), "vb200_batch_last_kernel_ms")
+        return a.value, b.value
+
 
 def RegistrationICPBatch(sources, scene, max_correspondence_distance, inits, estimation=None, criteria=None,
                          want_corr=True):

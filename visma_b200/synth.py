@@ -63,13 +63,15 @@ def make_T(R, t):
 
 
 def make_room_scene(n_scene, n_objects, pts_per_object, seed=20260117, room=(6.0, 3.0, 6.0),
-                    object_fraction=0.3, noise=0.002):
+                    object_fraction=0.3, noise=0.002, source_seed=0):
     """SURVEY §8d workload.  Returns dict with
        scene_xyz, scene_nrm  (N x 3 f64): floor (y = 0), four walls and the objects' surfaces, N(0, noise)
                              along the normal; gravity is -Y as in VISMA (src/annotation.cpp:84)
        sources  list of (M x 3 f64 points, M x 3 normals) in each object's MODEL frame
        T_gt     B x 4 x 4 model -> scene ground truth
        T_init   B x 4 x 4 ground truth composed with a perturbation (yaw +-5 deg, roll/pitch +-1 deg, +-3 cm)
+    source_seed changes only the source fragments and perturbations (ranks of a multi-GPU run share one
+    scene but each aligns its own fragments).
     """
     rng = np.random.default_rng(seed)
     V, F = load_chair()
@@ -108,11 +110,12 @@ def make_room_scene(n_scene, n_objects, pts_per_object, seed=20260117, room=(6.0
         R = rot_y(yaw)
         parts.append(p @ R.T + [cx, 0.0, cz]); norms.append(nn @ R.T)
         # the source fragment is sampled from the scaled CAD model in its own frame (rigid ground truth)
-        sp, sn = sample_mesh(Vs, F, pts_per_object, orng)
+        srng = np.random.default_rng([seed + 1 + b, 7919, source_seed])
+        sp, sn = sample_mesh(Vs, F, pts_per_object, srng)
         sources.append((sp, sn))
         Tr = make_T(R, [cx, 0.0, cz])
-        d = np.deg2rad(orng.uniform([-1, -5, -1], [1, 5, 1]))
-        Tp = make_T(rot_xyz(*d), orng.uniform(-0.03, 0.03, 3))
+        d = np.deg2rad(srng.uniform([-1, -5, -1], [1, 5, 1]))
+        Tp = make_T(rot_xyz(*d), srng.uniform(-0.03, 0.03, 3))
         # perturb about the object's own position so a 5 degree yaw does not swing it across the room
         C = make_T(np.eye(3), [cx, 0.0, cz])
         T_gt.append(Tr)
