@@ -107,8 +107,8 @@ int vo_render_depth(const float *V, int64_t nV, const int32_t *F, int64_t nF, co
 float vo_linearize_depth(float zb, float zn, float zf);
 
 /* ---- voxel down-sample (O3D/src/Core/Geometry/DownSample.cpp:179-220) ---------------------------- */
-/* Output sorted by voxel index (z-major) because the reference's order is unordered_map iteration
- * order; compare as sets.  Returns number of voxels, or -1 on the reference's error paths. */
+/* Output in order of each voxel's first point in the input (the reference's order is unordered_map
+ * iteration order: compare as sets).  Returns number of voxels, or -1 on the reference's error paths. */
 int64_t vo_voxel_downsample(const double *xyz, const double *nrm, int64_t n, double voxel,
                             double *out_xyz, double *out_nrm);
 

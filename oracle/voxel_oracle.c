@@ -44,6 +44,19 @@ int64_t vo_voxel_downsample(const double *xyz, const double *nrm, int64_t n, dou
         keys[i].idx = (int32_t)i;
     }
     qsort(keys, (size_t)n, sizeof(vkey), vkey_cmp);
+    /* voxels are emitted in order of FIRST APPEARANCE in the input (the reference's order is the
+     * unordered_map's, i.e. unspecified; callers compare as sets).  rank[i] = output slot of the voxel whose
+     * first point is i. */
+    int64_t *rank = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    memset(rank, 0, sizeof(int64_t) * (size_t)n);
+    for (int64_t s = 0; s < n; s++)
+        if (s == 0 || keys[s].v[0] != keys[s - 1].v[0] || keys[s].v[1] != keys[s - 1].v[1] ||
+            keys[s].v[2] != keys[s - 1].v[2])
+            rank[keys[s].idx] = 1;
+    {
+        int64_t run = 0;
+        for (int64_t i = 0; i < n; i++) { int64_t f = rank[i]; rank[i] = run; run += f; }
+    }
     int64_t nv = 0;
     for (int64_t s = 0; s < n;) {
         int64_t e = s;
@@ -57,14 +70,16 @@ int64_t vo_voxel_downsample(const double *xyz, const double *nrm, int64_t n, dou
             e++;
         }
         double cnt = (double)(e - s);
-        for (int a = 0; a < 3; a++) out_xyz[3 * nv + a] = p[a] / cnt; /* GetAveragePoint :66 */
+        int64_t o = rank[keys[s].idx];
+        for (int a = 0; a < 3; a++) out_xyz[3 * o + a] = p[a] / cnt; /* GetAveragePoint :66 */
         if (nrm && out_nrm) {
             double l = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);  /* normalized() :71 */
-            for (int a = 0; a < 3; a++) out_nrm[3 * nv + a] = l > 0.0 ? q[a] / l : q[a];
+            for (int a = 0; a < 3; a++) out_nrm[3 * o + a] = l > 0.0 ? q[a] / l : q[a];
         }
         nv++;
         s = e;
     }
     free(keys);
+    free(rank);
     return nv;
 }

@@ -1,0 +1,37 @@
+"""The C++ host adapters (visma_b200/host/*.h) compiled against the reference's real Open3D headers and run
+next to the reference's own CPU functions (oracle/_ref/dropin_check, built by `make -C oracle dropin`).
+Covers BASELINE config 1 (plumbing): the reference's CPU RegistrationICP loop driving the GPU estimator."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, small_scene
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(ROOT, "oracle", "_ref", "dropin_check")
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/dropin_check not built (needs /root/reference)")
+def test_cpp_dropin_against_reference(tmp_path):
+    d = small_scene(n_scene=100000, n_objects=2, m=50000, seed=21)  # config 1: one chair, one 50k fragment
+    src, sn = d["sources"][0]
+    f = tmp_path / "in.bin"
+    with open(f, "wb") as fh:
+        np.array([len(d["scene_xyz"]), len(src)], np.int64).tofile(fh)
+        for a in (d["scene_xyz"], d["scene_nrm"], src, sn, d["T_init"][0]):
+            np.ascontiguousarray(a, np.float64).tofile(fh)
+    out = subprocess.run([BIN, str(f)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("p2p", "p2plane"):
+        assert r[k]["dT"] < 1e-6, r[k]
+        assert abs(r[k]["ncorr_ref"] - r[k]["ncorr_gpu"]) <= 2 and abs(r[k]["rmse_ref"] - r[k]["rmse_gpu"]) < 1e-6
+    assert r["cicp_plugin"]["dT"] < 1e-9 and r["cicp_plugin"]["ncorr_ref"] == r["cicp_plugin"]["ncorr_mix"]
+    assert r["errors"]["bad_distance_dT"] == 0 and r["errors"]["no_normals_dT"] == 0
+    assert r["errors"]["no_normals_fitness"] == 0
+    assert r["voxel"]["n_ref"] == r["voxel"]["n_gpu"] and r["voxel"]["dsum"] < 1e-6
+    assert r["render"]["covered"] > 10000 and abs(r["render"]["z_lin"] - 1.0) < 1e-3

@@ -243,6 +243,103 @@ __device__ __forceinline__ int nn_search(const GridDev &G, const QueryCtx &c, do
     return nn_exact_rescan(G, c, qx, qy, qz, r2, fminf(r.best + 2.0f * bb, r2_ub), d2_out);
 }
 
+// ---- warp-cooperative search -----------------------------------------------------------------------------
+// The per-lane walk above diverges badly when the 32 lanes of a warp visit different cells (measured: 4.5 of
+// 32 lanes active per issued instruction).  When a warp's queries are spatially coherent — k_pass sorts the
+// source clouds for exactly that — the warp instead walks ONE box of fine cells that covers every lane's
+// reach: all loop bounds, the coarse-cell loads, the fine-cell ranges and the candidate loads are
+// warp-uniform (one broadcast load serves 32 queries) and each lane only keeps its own best / runner-up.
+// Scanning extra candidates never changes a lane's result, so the answers are those of the per-lane search.
+
+struct FineBox { int x0, x1, y0, y1, z0, z1; };
+
+__device__ __forceinline__ bool box_empty(const FineBox &b) { return b.x0 > b.x1 || b.y0 > b.y1 || b.z0 > b.z1; }
+
+// scan every occupied fine cell of `box` (minus `skip`, if given) with warp-uniform control flow
+template <bool PRUNE, bool HAS_SKIP>
+__device__ __forceinline__ void scan_box_uniform(const GridDev &G, const QueryCtx &c, bool valid, const FineBox &box,
+                                                 const FineBox &skip, float r2_ub, Screen &r) {
+    const GridParams &g = G.p;
+    const float fine2 = g.fine * g.fine;
+    for (int cz = box.z0 >> 2; cz <= (box.z1 >> 2); ++cz)
+        for (int cy = box.y0 >> 2; cy <= (box.y1 >> 2); ++cy)
+            for (int cx = box.x0 >> 2; cx <= (box.x1 >> 2); ++cx) {
+                const CoarseCell cc = G.coarse[((int64_t)cz * g.cdim[1] + cy) * g.cdim[0] + cx];
+                const unsigned long long m = cc.mask;
+                if (m == 0ull) continue;
+                unsigned long long sel = m & range_mask(max(box.x0 - 4 * cx, 0), min(box.x1 - 4 * cx, 3),
+                                                        max(box.y0 - 4 * cy, 0), min(box.y1 - 4 * cy, 3),
+                                                        max(box.z0 - 4 * cz, 0), min(box.z1 - 4 * cz, 3));
+                if (HAS_SKIP) {
+                    int ax = max(skip.x0 - 4 * cx, 0), bx = min(skip.x1 - 4 * cx, 3);
+                    int ay = max(skip.y0 - 4 * cy, 0), by = min(skip.y1 - 4 * cy, 3);
+                    int az = max(skip.z0 - 4 * cz, 0), bz = min(skip.z1 - 4 * cz, 3);
+                    if (ax <= bx && ay <= by && az <= bz) sel &= ~range_mask(ax, bx, ay, by, az, bz);
+                }
+                while (sel) {
+                    const int b = __ffsll((long long)sel) - 1;
+                    sel &= sel - 1ull;
+                    if (PRUNE) {
+                        // skip the cell only if NO lane can have its winner (or an ambiguous runner-up) in it
+                        const int ox = 4 * cx + (b & 3) - c.gx, oy = 4 * cy + ((b >> 2) & 3) - c.gy,
+                                  oz = 4 * cz + (b >> 4) - c.gz;
+                        const float ex = axis_gap(ox, c.fx), ey = axis_gap(oy, c.fy), ez = axis_gap(oz, c.fz);
+                        const float gap2 = (ex * ex + ey * ey + ez * ez) * fine2 * 0.9999f - 1e-12f * fine2;
+                        const bool need = valid && gap2 <= fminf(r.best + 2.0f * band(g, r.best), r2_ub);
+                        if (!__any_sync(0xffffffffu, need)) continue;
+                    }
+                    const int rank = __popcll(m & ((1ull << b) - 1ull));
+                    const int s0 = __ldg(G.fstart + cc.base + rank), s1 = __ldg(G.fstart + cc.base + rank + 1);
+                    scan_run(G.hi, s0, s1, c, r);
+                }
+            }
+}
+
+constexpr int kMaxWarpBoxCells = 125;  // beyond this the warp's queries are not coherent: per-lane walks
+
+// All 32 lanes of the warp must call this together.  `valid` = this lane has a query inside the grid.
+__device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, const QueryCtx &c, double qx, double qy,
+                                              double qz, double r2, float r2_ub, double *d2_out) {
+    const unsigned FULL = 0xffffffffu;
+    const GridParams &g = G.p;
+    *d2_out = 0.0;
+    if (!__any_sync(FULL, valid)) return -1;
+    FineBox b0;
+    b0.x0 = __reduce_min_sync(FULL, valid ? c.gx : 0x7fffffff); b0.x1 = __reduce_max_sync(FULL, valid ? c.gx : -0x7fffffff);
+    b0.y0 = __reduce_min_sync(FULL, valid ? c.gy : 0x7fffffff); b0.y1 = __reduce_max_sync(FULL, valid ? c.gy : -0x7fffffff);
+    b0.z0 = __reduce_min_sync(FULL, valid ? c.gz : 0x7fffffff); b0.z1 = __reduce_max_sync(FULL, valid ? c.gz : -0x7fffffff);
+    const long long cells0 = (long long)(b0.x1 - b0.x0 + 1) * (b0.y1 - b0.y0 + 1) * (b0.z1 - b0.z0 + 1);
+    if (cells0 > kMaxWarpBoxCells) return valid ? nn_search(G, c, qx, qy, qz, r2, r2_ub, d2_out) : -1;
+    Screen r;
+    r.best = r2_ub; r.second = 3.0e38f; r.bs = -1;
+    QueryCtx cq = c;
+    if (!valid) { cq.qx = 3.0e18f; cq.qy = 3.0e18f; cq.qz = 3.0e18f; }  // never the best of anything
+    // phase 1: the cells that contain the warp's queries — every lane gets a tight bound from its own cell
+    scan_box_uniform<false, false>(G, cq, valid, b0, b0, r2_ub, r);
+    // phase 2: grow the box to cover every lane's reach, skipping what phase 1 already scanned
+    const float reach2 = fminf(r.best + 2.0f * band(g, r.best), r2_ub);
+    const float rho = sqrtf(reach2) / g.fine * 1.00001f + 1e-6f;
+    FineBox b1;
+    b1.x0 = __reduce_min_sync(FULL, valid ? c.gx - (int)ceilf(fmaxf(rho - c.fx, 0.0f)) : 0x7fffffff);
+    b1.x1 = __reduce_max_sync(FULL, valid ? c.gx + (int)ceilf(fmaxf(rho - (1.0f - c.fx), 0.0f)) : -0x7fffffff);
+    b1.y0 = __reduce_min_sync(FULL, valid ? c.gy - (int)ceilf(fmaxf(rho - c.fy, 0.0f)) : 0x7fffffff);
+    b1.y1 = __reduce_max_sync(FULL, valid ? c.gy + (int)ceilf(fmaxf(rho - (1.0f - c.fy), 0.0f)) : -0x7fffffff);
+    b1.z0 = __reduce_min_sync(FULL, valid ? c.gz - (int)ceilf(fmaxf(rho - c.fz, 0.0f)) : 0x7fffffff);
+    b1.z1 = __reduce_max_sync(FULL, valid ? c.gz + (int)ceilf(fmaxf(rho - (1.0f - c.fz), 0.0f)) : -0x7fffffff);
+    b1.x0 = max(b1.x0, 0); b1.y0 = max(b1.y0, 0); b1.z0 = max(b1.z0, 0);
+    b1.x1 = min(b1.x1, g.fdim[0] - 1); b1.y1 = min(b1.y1, g.fdim[1] - 1); b1.z1 = min(b1.z1, g.fdim[2] - 1);
+    if (!box_empty(b1)) scan_box_uniform<true, true>(G, cq, valid, b1, b0, r2_ub, r);
+    if (!valid || r.bs < 0) return -1;
+    // decide in double (per lane)
+    const float bb = band(g, r.best);
+    if (r.second - r.best > bb + band(g, r.second)) {
+        const double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)r.bs);
+        if (d < r2) { *d2_out = d; return r.bs; }
+        return -1;
+    }
+    return nn_exact_rescan(G, c, qx, qy, qz, r2, fminf(r.best + 2.0f * bb, r2_ub), d2_out);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace vb

@@ -155,17 +155,20 @@ __global__ void __launch_bounds__(kPassTpb) k_pass(GridDev G, const double *__re
         const bool valid = local < task.count;
         bool matched = false;
         double d2 = 0.0, vs[3] = {0, 0, 0}, vt[3] = {0, 0, 0}, nt[3] = {0, 0, 0};
+        QueryCtx c;
+        bool inside = false;
         if (valid) {
             const double *p = src_xyz + 3 * (int64_t)(task.src_begin + local);
             const double px = p[0], py = p[1], pz = p[2];
             vs[0] = T[0] * px + T[1] * py + T[2] * pz + T[3];
             vs[1] = T[4] * px + T[5] * py + T[6] * pz + T[7];
             vs[2] = T[8] * px + T[9] * py + T[10] * pz + T[11];
-            QueryCtx c;
-            int bs = -1;
-            if (make_query(G.p, vs[0], vs[1], vs[2], c))
-                bs = nn_search(G, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, &d2);
-            matched = bs >= 0;
+            inside = make_query(G.p, vs[0], vs[1], vs[2], c);
+        }
+        // warp-cooperative search: every lane takes part, lanes without a query just ride along
+        const int bs = nn_search_warp(G, inside, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, &d2);
+        matched = bs >= 0;
+        if (valid) {
             int j = -1;
             if (matched) {
                 j = __ldg(G.orig + bs);
@@ -321,13 +324,20 @@ __global__ void __launch_bounds__(256) k_src_keys(const double *__restrict__ xyz
     atomicAdd(counts + kk, 1);
 }
 
-__global__ void __launch_bounds__(256) k_src_scatter(const int *__restrict__ key, int n,
-                                                     const int *__restrict__ start, int *__restrict__ cursor,
-                                                     int *__restrict__ sidx) {
+// sidx entries carry the point's fine sub-cell (1 bit per axis of the quarter-coarse index) above the point
+// index so the per-bucket sort orders a bucket by (sub-cell, index): fine-cell-sized spatial coherence
+constexpr int kSubShift = 28;
+
+__global__ void __launch_bounds__(256) k_src_scatter(const double *__restrict__ xyz, const int *__restrict__ key,
+                                                     int n, double inv_fine, const int *__restrict__ start,
+                                                     int *__restrict__ cursor, int *__restrict__ sidx) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int kk = key[i];
-    sidx[start[kk] + atomicAdd(cursor + kk, 1)] = i;
+    int sx = (int)floor(xyz[3 * (int64_t)i] * inv_fine) & 1;
+    int sy = (int)floor(xyz[3 * (int64_t)i + 1] * inv_fine) & 1;
+    int sz = (int)floor(xyz[3 * (int64_t)i + 2] * inv_fine) & 1;
+    sidx[start[kk] + atomicAdd(cursor + kk, 1)] = ((sz * 4 + sy * 2 + sx) << kSubShift) | i;
 }
 
 __global__ void __launch_bounds__(128) k_src_sort_buckets(int nbuckets, const int *__restrict__ start,
@@ -344,7 +354,7 @@ __global__ void __launch_bounds__(256) k_src_gather(const double *__restrict__ i
                                                     double *__restrict__ out, int *__restrict__ orig) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    int i = sidx[s];
+    int i = sidx[s] & ((1 << kSubShift) - 1);
     out[3 * (int64_t)s] = in[3 * (int64_t)i];
     out[3 * (int64_t)s + 1] = in[3 * (int64_t)i + 1];
     out[3 * (int64_t)s + 2] = in[3 * (int64_t)i + 2];
@@ -467,6 +477,7 @@ static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int
         b->cloud_off[c] = (int)o;
     }
     const int n = b->cloud_off[ncloud];
+    if (n >= (1 << kSubShift)) return VB200_ERR_INVALID;  // 2^28 source points per batch
     b->npts = n;
     VB_CUDA(cudaMalloc((void **)&b->d_cloud_off, sizeof(int) * ((size_t)ncloud + 1)));
     VB_CUDA(cudaMemcpyAsync(b->d_cloud_off, b->cloud_off.data(), sizeof(int) * ((size_t)ncloud + 1),
@@ -488,7 +499,7 @@ static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int
     k_src_keys<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, b->d_cloud_off, ncloud, inv_half, d_key.p, d_counts.p);
     VB_TRY(exclusive_scan_i32(d_counts.p, d_start.p, (int64_t)nb, nullptr, st));
     VB_CUDA(cudaMemsetAsync(d_counts.p, 0, sizeof(int) * nb, st));
-    k_src_scatter<<<div_up(n, 256), 256, 0, st>>>(d_key.p, n, d_start.p, d_counts.p, d_sidx.p);
+    k_src_scatter<<<div_up(n, 256), 256, 0, st>>>(d_in.p, d_key.p, n, 4.0 / sc->grid.p.cell, d_start.p, d_counts.p, d_sidx.p);
     k_src_sort_buckets<<<div_up((int64_t)nb - 1, 128), 128, 0, st>>>((int)nb - 1, d_start.p, d_sidx.p);
     k_src_gather<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, d_sidx.p, b->d_cloud_off, ncloud, b->d_src, b->d_src_orig);
     VB_CUDA(cudaGetLastError());

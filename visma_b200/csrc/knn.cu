@@ -16,15 +16,20 @@ constexpr int kTpb = 256;
 __global__ void __launch_bounds__(kTpb) k_knn1(GridDev G, const double *__restrict__ q, int64_t nq, double r2,
                                                float r2_ub, int *__restrict__ out_idx,
                                                double *__restrict__ out_d2) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    const double x = q[3 * i], y = q[3 * i + 1], z = q[3 * i + 2];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < nq;  // whole warps stay alive: the search is warp-cooperative
+    double x = 0.0, y = 0.0, z = 0.0, d2 = 0.0;
     QueryCtx c;
-    int bs = -1;
-    double d2 = 0.0;
-    if (make_query(G.p, x, y, z, c)) bs = nn_search(G, c, x, y, z, r2, r2_ub, &d2);
-    out_idx[i] = bs >= 0 ? __ldg(G.orig + bs) : -1;
-    out_d2[i] = bs >= 0 ? d2 : 0.0;
+    bool inside = false;
+    if (live) {
+        x = q[3 * i]; y = q[3 * i + 1]; z = q[3 * i + 2];
+        inside = make_query(G.p, x, y, z, c);
+    }
+    const int bs = nn_search_warp(G, inside, c, x, y, z, r2, r2_ub, &d2);
+    if (live) {
+        out_idx[i] = bs >= 0 ? __ldg(G.orig + bs) : -1;
+        out_d2[i] = bs >= 0 ? d2 : 0.0;
+    }
 }
 
 

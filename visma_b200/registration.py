@@ -142,7 +142,8 @@ class Batch:
         self.scene = scene
         pts = [_f64(s.points_ if isinstance(s, PointCloud) else s) for s in sources]
         if with_normals is None:
-            with_normals = all(isinstance(s, PointCloud) and s.HasNormals() for s in sources) and len(sources) > 0
+            with_normals = len(sources) > 0 and all((isinstance(s, PointCloud) and s.HasNormals()) or len(p) == 0
+                                                    for s, p in zip(sources, pts))
         self.sizes = [len(p) for p in pts]
         off = np.zeros(len(pts) + 1, np.int64)
         off[1:] = np.cumsum(self.sizes)
@@ -231,7 +232,10 @@ def RegistrationICPBatch(sources, scene, max_correspondence_distance, inits, est
     criteria = criteria or ICPConvergenceCriteria()
     B = len(sources)
     pts = [_f64(s.points_ if isinstance(s, PointCloud) else s) for s in sources]
-    has_n = B > 0 and all(isinstance(s, PointCloud) and s.HasNormals() for s in sources)
+    # an empty source cannot "have normals" in Open3D's sense and the reference would return init for it
+    # either way; it must not switch the whole batch to the no-normals error path
+    has_n = B > 0 and all((isinstance(s, PointCloud) and s.HasNormals()) or len(p) == 0
+                          for s, p in zip(sources, pts))
     off = np.zeros(B + 1, np.int64)
     off[1:] = np.cumsum([len(p) for p in pts])
     xyz = _f64(np.concatenate(pts).reshape(-1, 3)) if B else np.zeros((0, 3))
