@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvisma_b200.so")
+# VISMA_B200_LIB: developer override to A/B an alternative build of the same CUDA library
+LIB_PATH = os.environ.get("VISMA_B200_LIB") or os.path.join(_HERE, "libvisma_b200.so")
 
 OK = 0
 ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_NORMALS, ERR_DISTANCE = -1, -2, -3, -4, -5, -6

@@ -244,23 +244,40 @@ __device__ __forceinline__ int nn_search(const GridDev &G, const QueryCtx &c, do
 }
 
 // ---- warp-cooperative search -----------------------------------------------------------------------------
-// The per-lane walk above diverges badly when the 32 lanes of a warp visit different cells (measured: 4.5 of
-// 32 lanes active per issued instruction).  When a warp's queries are spatially coherent — k_pass sorts the
-// source clouds for exactly that — the warp instead walks ONE box of fine cells that covers every lane's
-// reach: all loop bounds, the coarse-cell loads, the fine-cell ranges and the candidate loads are
-// warp-uniform (one broadcast load serves 32 queries) and each lane only keeps its own best / runner-up.
-// Scanning extra candidates never changes a lane's result, so the answers are those of the per-lane search.
+// A per-lane cell walk diverges badly when the 32 lanes of a warp visit different cells (first version,
+// measured: 4.5 of 32 lanes active per issued instruction).  Instead the warp repeatedly picks a leader lane,
+// groups the pending lanes whose home cell is within +-2 fine cells of the leader's, and walks ONE box of fine
+// cells that covers every group member's reach: all loop bounds, the coarse-cell loads, the fine-cell ranges
+// and the candidate loads are warp-uniform (one broadcast load serves the whole group) and each lane only
+// keeps its own best / runner-up.  Scanning extra candidates never changes a lane's result, so the answers
+// are those of an independent per-query search.  k_pass sorts every source cloud spatially so that a warp is
+// normally one or two groups.
 
 struct FineBox { int x0, x1, y0, y1, z0, z1; };
 
 __device__ __forceinline__ bool box_empty(const FineBox &b) { return b.x0 > b.x1 || b.y0 > b.y1 || b.z0 > b.z1; }
 
+// small non-negative int -> float without the (quarter-rate) I2F conversion unit
+__device__ __forceinline__ float small_int_to_float(int v) { return __int_as_float(0x4B000000 | v) - 8388608.0f; }
+
+// upper bound of best + 2*band(best), capped at the acceptance bound (fast reciprocal sqrt, padded)
+__device__ __forceinline__ float reach_of(const GridParams &g, float best, float r2_ub) {
+    const float b = fmaxf(best, 1e-30f);
+    const float bnd = fmaf(g.band_a * 1.0001f, b * rsqrtf(b), fmaf(g.band_rel, b, g.band_b));
+    return fminf(fmaf(2.0f, bnd, best), r2_ub);
+}
+
+// lane position in absolute fine-cell units (cell index + fraction); resolution 2^-12 cell or better, which
+// the 1e-3 relative deflation of the gap below absorbs
+struct LanePos { float ux, uy, uz; };
+
 // scan every occupied fine cell of `box` (minus `skip`, if given) with warp-uniform control flow
 template <bool PRUNE, bool HAS_SKIP>
-__device__ __forceinline__ void scan_box_uniform(const GridDev &G, const QueryCtx &c, bool valid, const FineBox &box,
-                                                 const FineBox &skip, float r2_ub, Screen &r) {
+__device__ __forceinline__ void scan_box_uniform(const GridDev &G, const QueryCtx &c, const LanePos &lp, bool member,
+                                                 const FineBox &box, const FineBox &skip, float r2_ub, Screen &r) {
     const GridParams &g = G.p;
-    const float fine2 = g.fine * g.fine;
+    const float fine2 = g.fine * g.fine * 0.998f;  // deflated: never prune a cell that could matter
+    float thr = reach_of(g, r.best, r2_ub);
     for (int cz = box.z0 >> 2; cz <= (box.z1 >> 2); ++cz)
         for (int cy = box.y0 >> 2; cy <= (box.y1 >> 2); ++cy)
             for (int cx = box.x0 >> 2; cx <= (box.x1 >> 2); ++cx) {
@@ -276,26 +293,31 @@ __device__ __forceinline__ void scan_box_uniform(const GridDev &G, const QueryCt
                     int az = max(skip.z0 - 4 * cz, 0), bz = min(skip.z1 - 4 * cz, 3);
                     if (ax <= bx && ay <= by && az <= bz) sel &= ~range_mask(ax, bx, ay, by, az, bz);
                 }
+                if (sel == 0ull) continue;
+                // lane position relative to this coarse cell's corner, fine-cell units
+                const float rx = lp.ux - (float)(4 * cx), ry = lp.uy - (float)(4 * cy), rz = lp.uz - (float)(4 * cz);
                 while (sel) {
                     const int b = __ffsll((long long)sel) - 1;
                     sel &= sel - 1ull;
                     if (PRUNE) {
-                        // skip the cell only if NO lane can have its winner (or an ambiguous runner-up) in it
-                        const int ox = 4 * cx + (b & 3) - c.gx, oy = 4 * cy + ((b >> 2) & 3) - c.gy,
-                                  oz = 4 * cz + (b >> 4) - c.gz;
-                        const float ex = axis_gap(ox, c.fx), ey = axis_gap(oy, c.fy), ez = axis_gap(oz, c.fz);
-                        const float gap2 = (ex * ex + ey * ey + ez * ez) * fine2 * 0.9999f - 1e-12f * fine2;
-                        const bool need = valid && gap2 <= fminf(r.best + 2.0f * band(g, r.best), r2_ub);
-                        if (!__any_sync(0xffffffffu, need)) continue;
+                        // skip the cell only if NO member can have its winner (or an ambiguous runner-up) in it
+                        const float fx = small_int_to_float(b & 3), fy = small_int_to_float((b >> 2) & 3),
+                                    fz = small_int_to_float(b >> 4);
+                        const float ex = fmaxf(fmaxf(fx - rx, rx - fx - 1.0f), 0.0f);
+                        const float ey = fmaxf(fmaxf(fy - ry, ry - fy - 1.0f), 0.0f);
+                        const float ez = fmaxf(fmaxf(fz - rz, rz - fz - 1.0f), 0.0f);
+                        const float gap2 = (ex * ex + ey * ey + ez * ez) * fine2;
+                        if (!__any_sync(0xffffffffu, member && gap2 <= thr)) continue;
                     }
                     const int rank = __popcll(m & ((1ull << b) - 1ull));
                     const int s0 = __ldg(G.fstart + cc.base + rank), s1 = __ldg(G.fstart + cc.base + rank + 1);
                     scan_run(G.hi, s0, s1, c, r);
+                    if (PRUNE) thr = reach_of(g, r.best, r2_ub);
                 }
             }
 }
 
-constexpr int kMaxWarpBoxCells = 125;  // beyond this the warp's queries are not coherent: per-lane walks
+constexpr int kGroupHalfWidth = 2;  // lanes within +-2 fine cells of the leader are searched together
 
 // All 32 lanes of the warp must call this together.  `valid` = this lane has a query inside the grid.
 __device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, const QueryCtx &c, double qx, double qy,
@@ -303,32 +325,43 @@ __device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, cons
     const unsigned FULL = 0xffffffffu;
     const GridParams &g = G.p;
     *d2_out = 0.0;
-    if (!__any_sync(FULL, valid)) return -1;
-    FineBox b0;
-    b0.x0 = __reduce_min_sync(FULL, valid ? c.gx : 0x7fffffff); b0.x1 = __reduce_max_sync(FULL, valid ? c.gx : -0x7fffffff);
-    b0.y0 = __reduce_min_sync(FULL, valid ? c.gy : 0x7fffffff); b0.y1 = __reduce_max_sync(FULL, valid ? c.gy : -0x7fffffff);
-    b0.z0 = __reduce_min_sync(FULL, valid ? c.gz : 0x7fffffff); b0.z1 = __reduce_max_sync(FULL, valid ? c.gz : -0x7fffffff);
-    const long long cells0 = (long long)(b0.x1 - b0.x0 + 1) * (b0.y1 - b0.y0 + 1) * (b0.z1 - b0.z0 + 1);
-    if (cells0 > kMaxWarpBoxCells) return valid ? nn_search(G, c, qx, qy, qz, r2, r2_ub, d2_out) : -1;
     Screen r;
     r.best = r2_ub; r.second = 3.0e38f; r.bs = -1;
-    QueryCtx cq = c;
-    if (!valid) { cq.qx = 3.0e18f; cq.qy = 3.0e18f; cq.qz = 3.0e18f; }  // never the best of anything
-    // phase 1: the cells that contain the warp's queries — every lane gets a tight bound from its own cell
-    scan_box_uniform<false, false>(G, cq, valid, b0, b0, r2_ub, r);
-    // phase 2: grow the box to cover every lane's reach, skipping what phase 1 already scanned
-    const float reach2 = fminf(r.best + 2.0f * band(g, r.best), r2_ub);
-    const float rho = sqrtf(reach2) / g.fine * 1.00001f + 1e-6f;
-    FineBox b1;
-    b1.x0 = __reduce_min_sync(FULL, valid ? c.gx - (int)ceilf(fmaxf(rho - c.fx, 0.0f)) : 0x7fffffff);
-    b1.x1 = __reduce_max_sync(FULL, valid ? c.gx + (int)ceilf(fmaxf(rho - (1.0f - c.fx), 0.0f)) : -0x7fffffff);
-    b1.y0 = __reduce_min_sync(FULL, valid ? c.gy - (int)ceilf(fmaxf(rho - c.fy, 0.0f)) : 0x7fffffff);
-    b1.y1 = __reduce_max_sync(FULL, valid ? c.gy + (int)ceilf(fmaxf(rho - (1.0f - c.fy), 0.0f)) : -0x7fffffff);
-    b1.z0 = __reduce_min_sync(FULL, valid ? c.gz - (int)ceilf(fmaxf(rho - c.fz, 0.0f)) : 0x7fffffff);
-    b1.z1 = __reduce_max_sync(FULL, valid ? c.gz + (int)ceilf(fmaxf(rho - (1.0f - c.fz), 0.0f)) : -0x7fffffff);
-    b1.x0 = max(b1.x0, 0); b1.y0 = max(b1.y0, 0); b1.z0 = max(b1.z0, 0);
-    b1.x1 = min(b1.x1, g.fdim[0] - 1); b1.y1 = min(b1.y1, g.fdim[1] - 1); b1.z1 = min(b1.z1, g.fdim[2] - 1);
-    if (!box_empty(b1)) scan_box_uniform<true, true>(G, cq, valid, b1, b0, r2_ub, r);
+    LanePos lp;
+    lp.ux = (float)c.gx + c.fx; lp.uy = (float)c.gy + c.fy; lp.uz = (float)c.gz + c.fz;
+    const int lane = threadIdx.x & 31;
+    unsigned pending = __ballot_sync(FULL, valid);
+    while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const int lgx = __shfl_sync(FULL, c.gx, leader), lgy = __shfl_sync(FULL, c.gy, leader),
+                  lgz = __shfl_sync(FULL, c.gz, leader);
+        const bool member = ((pending >> lane) & 1u) && abs(c.gx - lgx) <= kGroupHalfWidth &&
+                            abs(c.gy - lgy) <= kGroupHalfWidth && abs(c.gz - lgz) <= kGroupHalfWidth;
+        pending &= ~__ballot_sync(FULL, member);
+        QueryCtx cq = c;
+        Screen rr;
+        rr.best = r2_ub; rr.second = 3.0e38f; rr.bs = -1;
+        if (!member) { cq.qx = 3.0e18f; cq.qy = 3.0e18f; cq.qz = 3.0e18f; }  // never the best of anything
+        // phase 1: the cells that contain the group's queries — every member gets a tight bound from its own cell
+        FineBox b0;
+        b0.x0 = __reduce_min_sync(FULL, member ? c.gx : 0x7fffffff); b0.x1 = __reduce_max_sync(FULL, member ? c.gx : -0x7fffffff);
+        b0.y0 = __reduce_min_sync(FULL, member ? c.gy : 0x7fffffff); b0.y1 = __reduce_max_sync(FULL, member ? c.gy : -0x7fffffff);
+        b0.z0 = __reduce_min_sync(FULL, member ? c.gz : 0x7fffffff); b0.z1 = __reduce_max_sync(FULL, member ? c.gz : -0x7fffffff);
+        scan_box_uniform<false, false>(G, cq, lp, member, b0, b0, r2_ub, rr);
+        // phase 2: grow the box to cover every member's reach, skipping what phase 1 already scanned
+        const float rho = sqrtf(reach_of(g, rr.best, r2_ub)) / g.fine * 1.001f + 1e-4f;
+        FineBox b1;
+        b1.x0 = __reduce_min_sync(FULL, member ? c.gx - (int)ceilf(fmaxf(rho - c.fx, 0.0f)) : 0x7fffffff);
+        b1.x1 = __reduce_max_sync(FULL, member ? c.gx + (int)ceilf(fmaxf(rho - (1.0f - c.fx), 0.0f)) : -0x7fffffff);
+        b1.y0 = __reduce_min_sync(FULL, member ? c.gy - (int)ceilf(fmaxf(rho - c.fy, 0.0f)) : 0x7fffffff);
+        b1.y1 = __reduce_max_sync(FULL, member ? c.gy + (int)ceilf(fmaxf(rho - (1.0f - c.fy), 0.0f)) : -0x7fffffff);
+        b1.z0 = __reduce_min_sync(FULL, member ? c.gz - (int)ceilf(fmaxf(rho - c.fz, 0.0f)) : 0x7fffffff);
+        b1.z1 = __reduce_max_sync(FULL, member ? c.gz + (int)ceilf(fmaxf(rho - (1.0f - c.fz), 0.0f)) : -0x7fffffff);
+        b1.x0 = max(b1.x0, 0); b1.y0 = max(b1.y0, 0); b1.z0 = max(b1.z0, 0);
+        b1.x1 = min(b1.x1, g.fdim[0] - 1); b1.y1 = min(b1.y1, g.fdim[1] - 1); b1.z1 = min(b1.z1, g.fdim[2] - 1);
+        if (!box_empty(b1)) scan_box_uniform<true, true>(G, cq, lp, member, b1, b0, r2_ub, rr);
+        if (member) r = rr;
+    }
     if (!valid || r.bs < 0) return -1;
     // decide in double (per lane)
     const float bb = band(g, r.best);

@@ -32,6 +32,9 @@ namespace vb {
 
 namespace {
 
+#ifndef VB_PASS_MINBLOCKS
+#define VB_PASS_MINBLOCKS 3  // resident k_pass blocks per SM the register budget is tuned for
+#endif
 constexpr int kPassTpb = 256;
 constexpr int kPtsPerThread = 4;
 constexpr int kChunk = kPassTpb * kPtsPerThread;  // source points per block
@@ -130,7 +133,7 @@ __device__ __forceinline__ void contributions(bool matched, double d2, const dou
 // One ICP correspondence pass for every active problem: transform + radius-bounded 1-NN + estimator
 // products + block reduction.  grid = one block per kChunk source points of one problem.
 template <int MODE>
-__global__ void __launch_bounds__(kPassTpb) k_pass(GridDev G, const double *__restrict__ src_xyz,
+__global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass(GridDev G, const double *__restrict__ src_xyz,
                                                    const BlockTask *__restrict__ tasks,
                                                    const ProbState *__restrict__ states,
                                                    double *__restrict__ partials, int *__restrict__ corr_j,

@@ -1,0 +1,70 @@
+"""Multi-GPU sharding of the ICP path: one process per GPU, objects round-robin over ranks, the scene
+replicated, and ONE collective — an all-gather of the final pose table.  Each object's solve is
+independent (src/annotation.cpp:103-141), so there is no data-path exchange to fuse with a kernel.
+
+torch.distributed is plumbing only (NCCL over NVLink on the GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+
+ROW = 20  # T (16, row-major) + fitness + rmse + ncorr + iterations
+
+
+def shard_objects(n_objects, rank, world):
+    """Objects owned by `rank`: {b : b mod world == rank}.  All yaw initialisations of an object stay on its
+    rank so RegisterModelToScene's arg-max (src/annotation.cpp:59-61) is local."""
+    return list(range(rank, n_objects, world))
+
+
+def rows_per_rank(n_objects, world):
+    return (n_objects + world - 1) // world
+
+
+def pack_results(results, n_objects, rank, world):
+    """results: list of RegistrationResult for shard_objects(...) in order -> padded [rows_per_rank, ROW]."""
+    out = np.zeros((rows_per_rank(n_objects, world), ROW), np.float64)
+    for k, r in enumerate(results):
+        out[k, :16] = np.asarray(r.transformation_).reshape(-1)
+        out[k, 16] = r.fitness_
+        out[k, 17] = r.inlier_rmse_
+        out[k, 18] = len(r.correspondence_set_)
+        out[k, 19] = r.iterations_
+    return out
+
+
+def unpack_table(gathered, n_objects, world):
+    """gathered: [world, rows_per_rank, ROW] -> [n_objects, ROW] in object order."""
+    table = np.zeros((n_objects, ROW), np.float64)
+    for r in range(world):
+        for k, b in enumerate(shard_objects(n_objects, r, world)):
+            table[b] = gathered[r, k]
+    return table
+
+
+def all_gather_poses(local_rows, n_objects, device=None, group=None):
+    """The path's single collective.  local_rows: this rank's padded [rows_per_rank, ROW] table.
+    Returns the full [n_objects, ROW] table on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    t = torch.from_numpy(np.ascontiguousarray(local_rows))
+    if device is not None:
+        t = t.to(device)
+    if world == 1:
+        return unpack_table(t.cpu().numpy()[None], n_objects, 1)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return unpack_table(torch.stack(out).cpu().numpy(), n_objects, world)
+
+
+def register_sharded(scene, sources, inits, max_dist, estimation, criteria=None, device=None, group=None):
+    """Run this rank's share of a global list of ICP problems and all-gather the pose table.
+    sources / inits are the GLOBAL lists (every rank sees the same ones); returns [n_objects, ROW]."""
+    import torch.distributed as dist
+    from . import registration as reg
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    mine = shard_objects(len(sources), rank, world)
+    res = reg.RegistrationICPBatch([sources[b] for b in mine], scene, max_dist,
+                                   np.asarray([inits[b] for b in mine]).reshape(-1, 4, 4), estimation, criteria,
+                                   want_corr=False) if mine else []
+    return all_gather_poses(pack_results(res, len(sources), rank, world), len(sources), device, group)
