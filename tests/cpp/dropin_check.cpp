@@ -5,13 +5,26 @@
 //
 //   usage: dropin_check <input.bin>      prints one JSON object with the differences
 //   input: int64 n_tgt, n_src; tgt xyz, tgt nrm, src xyz, src nrm (doubles); init (16 doubles, row-major)
+#include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #define VISMA_B200_WITH_CICP
 #include "registration_b200.h"
 #include "renderer_b200.h"
+
+// Open3D's PrintError writes (coloured) text to stdout, so the JSON is collected and emitted last, alone on a line
+static std::string g_json;
+static void out(const char *fmt, ...) {
+    char buf[2048];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_json += buf;
+}
 
 static double max_abs_diff(const Eigen::Matrix4d &a, const Eigen::Matrix4d &b) {
     double m = 0;
@@ -39,7 +52,7 @@ int main(int argc, char **argv) {
     Eigen::Matrix4d init = visma_b200::FromRowMajor(init_rm);
     const double max_d = 0.075;
 
-    printf("{");
+    out("{");
     // (1) the ICP operator: reference CPU vs the drop-in, both estimators
     open3d::TransformationEstimationPointToPoint p2p;
     open3d::TransformationEstimationPointToPlane p2l;
@@ -48,7 +61,7 @@ int main(int argc, char **argv) {
     for (int e = 0; e < 2; e++) {
         auto ref = open3d::RegistrationICP(source, target, max_d, init, *ests[e]);
         auto gpu = visma_b200::RegistrationICP(source, target, max_d, init, *ests[e]);
-        printf("\"%s\": {\"dT\": %.3e, \"fitness_ref\": %.17g, \"fitness_gpu\": %.17g, \"rmse_ref\": %.17g, "
+        out("\"%s\": {\"dT\": %.3e, \"fitness_ref\": %.17g, \"fitness_gpu\": %.17g, \"rmse_ref\": %.17g, "
                "\"rmse_gpu\": %.17g, \"ncorr_ref\": %zu, \"ncorr_gpu\": %zu}, ",
                names[e], max_abs_diff(ref.transformation_, gpu.transformation_), ref.fitness_, gpu.fitness_,
                ref.inlier_rmse_, gpu.inlier_rmse_, ref.correspondence_set_.size(), gpu.correspondence_set_.size());
@@ -58,7 +71,7 @@ int main(int argc, char **argv) {
         open3d::cicp::TransformationEstimationPointToPoint4DoFB200 gpu_est;
         auto ref = open3d::RegistrationICP(source, target, max_d, init, p2p);
         auto mix = open3d::RegistrationICP(source, target, max_d, init, gpu_est);
-        printf("\"cicp_plugin\": {\"dT\": %.3e, \"ncorr_ref\": %zu, \"ncorr_mix\": %zu}, ",
+        out("\"cicp_plugin\": {\"dT\": %.3e, \"ncorr_ref\": %zu, \"ncorr_mix\": %zu}, ",
                max_abs_diff(ref.transformation_, mix.transformation_), ref.correspondence_set_.size(),
                mix.correspondence_set_.size());
     }
@@ -68,7 +81,7 @@ int main(int argc, char **argv) {
         open3d::PointCloud bare;
         bare.points_ = source.points_;
         auto b = visma_b200::RegistrationICP(bare, target, max_d, init, p2l);
-        printf("\"errors\": {\"bad_distance_dT\": %.3e, \"no_normals_dT\": %.3e, \"no_normals_fitness\": %g}, ",
+        out("\"errors\": {\"bad_distance_dT\": %.3e, \"no_normals_dT\": %.3e, \"no_normals_fitness\": %g}, ",
                max_abs_diff(a.transformation_, init), max_abs_diff(b.transformation_, init), b.fitness_);
     }
     // (4) VoxelDownSample: same point set as the reference (order differs: unordered_map vs voxel index)
@@ -78,7 +91,7 @@ int main(int argc, char **argv) {
         double sr[3] = {0, 0, 0}, sg[3] = {0, 0, 0};
         for (auto &p : ref->points_) for (int a = 0; a < 3; a++) sr[a] += p[a];
         for (auto &p : gpu->points_) for (int a = 0; a < 3; a++) sg[a] += p[a];
-        printf("\"voxel\": {\"n_ref\": %zu, \"n_gpu\": %zu, \"dsum\": %.3e}, ", ref->points_.size(),
+        out("\"voxel\": {\"n_ref\": %zu, \"n_gpu\": %zu, \"dsum\": %.3e}, ", ref->points_.size(),
                gpu->points_.size(), std::abs(sr[0] - sg[0]) + std::abs(sr[1] - sg[1]) + std::abs(sr[2] - sg[2]));
     }
     // (5) the Renderer class compiles with the reference's call sequence (render/tools/render_depth.cpp:30-47)
@@ -96,9 +109,10 @@ int main(int argc, char **argv) {
         int covered = 0;
         float zmin = 1.f;
         for (float z : depth) if (z < 1.f) { covered++; zmin = std::min(zmin, z); }
-        printf("\"render\": {\"covered\": %d, \"z_lin\": %.6f}", covered,
+        out("\"render\": {\"covered\": %d, \"z_lin\": %.6f}", covered,
                visma_b200::LinearizeDepth<float>(zmin, 0.05f, 10.0f));
     }
-    printf("}\n");
+    out("}");
+    printf("\nJSON:%s\n", g_json.c_str());
     return 0;
 }

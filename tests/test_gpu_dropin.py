@@ -26,8 +26,8 @@ def test_cpp_dropin_against_reference(tmp_path):
             np.ascontiguousarray(a, np.float64).tofile(fh)
     out = subprocess.run([BIN, str(f)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
-    line = out.stdout.strip().splitlines()[-1]
-    r = json.loads(line[line.index("{"):])  # Open3D's PrintError leaves a colour-reset escape on stdout
+    line = [l for l in out.stdout.splitlines() if l.startswith("JSON:")][-1]
+    r = json.loads(line[5:])
     for k in ("p2p", "p2plane"):
         assert r[k]["dT"] < 1e-6, r[k]
         assert abs(r[k]["ncorr_ref"] - r[k]["ncorr_gpu"]) <= 2 and abs(r[k]["rmse_ref"] - r[k]["rmse_gpu"]) < 1e-6

@@ -34,12 +34,18 @@ constexpr int kNumSMsB200 = 148;
 
 inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// Device buffer with RAII so early returns do not leak.
+// Device buffer with RAII so early returns do not leak.  Constructed with a stream it uses the
+// stream-ordered allocator (cudaMallocAsync / cudaFreeAsync): with the pool's release threshold raised in
+// select_device() repeated calls reuse the same memory instead of paying cudaMalloc/cudaFree (which
+// synchronise the device) on every vb200_icp_run.
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    cudaStream_t st = nullptr;
+    bool async = false;
     DevBuf() {}
+    explicit DevBuf(cudaStream_t s) : st(s), async(true) {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
@@ -47,10 +53,12 @@ struct DevBuf {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc((void **)&p, count * sizeof(T));
+        return async ? cudaMallocAsync((void **)&p, count * sizeof(T), st) : cudaMalloc((void **)&p, count * sizeof(T));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (async) cudaFreeAsync(p, st); else cudaFree(p);
+        }
         p = nullptr;
         n = 0;
     }

@@ -123,18 +123,20 @@ struct Screen {
 
 __device__ __forceinline__ void scan_run(const float4 *__restrict__ hi, int s0, int s1, const QueryCtx &c,
                                          Screen &r) {
-    for (int s = s0; s < s1; ++s) {
-        float4 t = __ldg(hi + s);
-        float dx = c.qx - t.x, dy = c.qy - t.y, dz = c.qz - t.z;
-        float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d < r.best) {
-            r.second = r.best;
-            r.best = d;
-            r.bs = s;
-        } else {
-            r.second = fminf(r.second, d);
-        }
+    auto consider = [&](const float4 t, int s) {
+        const float dx = c.qx - t.x, dy = c.qy - t.y, dz = c.qz - t.z;
+        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const bool lt = d < r.best;
+        r.second = lt ? r.best : fminf(r.second, d);  // equal distances land in `second`: flagged ambiguous
+        r.bs = lt ? s : r.bs;
+        r.best = fminf(r.best, d);
+    };
+    int s = s0;
+    for (; s + 3 < s1; s += 4) {  // four independent 16-byte loads in flight per iteration
+        const float4 t0 = __ldg(hi + s), t1 = __ldg(hi + s + 1), t2 = __ldg(hi + s + 2), t3 = __ldg(hi + s + 3);
+        consider(t0, s); consider(t1, s + 1); consider(t2, s + 2); consider(t3, s + 3);
     }
+    for (; s < s1; ++s) consider(__ldg(hi + s), s);
 }
 
 template <class Visit>

@@ -455,7 +455,10 @@ struct Batch {
 };
 
 static void batch_free_problems(Batch *b) {
-    cudaFree(b->d_probs); cudaFree(b->d_states); cudaFree(b->d_tasks); cudaFree(b->d_partials); cudaFree(b->d_corr);
+    cudaStream_t st = b->scene->stream;
+    void *ptrs[5] = {b->d_probs, b->d_states, b->d_tasks, b->d_partials, b->d_corr};
+    for (void *q : ptrs)
+        if (q) cudaFreeAsync(q, st);
     b->d_probs = nullptr; b->d_states = nullptr; b->d_tasks = nullptr; b->d_partials = nullptr; b->d_corr = nullptr;
     b->P = 0; b->nblk = 0; b->probs.clear();
 }
@@ -465,7 +468,10 @@ static void batch_free(Batch *b) {
     batch_free_problems(b);
     for (int i = 0; i < 3; i++)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);
-    cudaFree(b->d_src); cudaFree(b->d_src_orig); cudaFree(b->d_cloud_off);
+    cudaStream_t st = b->scene->stream;
+    void *ptrs[3] = {b->d_src, b->d_src_orig, b->d_cloud_off};
+    for (void *q : ptrs)
+        if (q) cudaFreeAsync(q, st);
     delete b;
 }
 
@@ -482,14 +488,14 @@ static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int
     const int n = b->cloud_off[ncloud];
     if (n >= (1 << kSubShift)) return VB200_ERR_INVALID;  // 2^28 source points per batch
     b->npts = n;
-    VB_CUDA(cudaMalloc((void **)&b->d_cloud_off, sizeof(int) * ((size_t)ncloud + 1)));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_cloud_off, sizeof(int) * ((size_t)ncloud + 1), st));
     VB_CUDA(cudaMemcpyAsync(b->d_cloud_off, b->cloud_off.data(), sizeof(int) * ((size_t)ncloud + 1),
                             cudaMemcpyHostToDevice, st));
-    VB_CUDA(cudaMalloc((void **)&b->d_src, sizeof(double) * 3 * (size_t)std::max(n, 1)));
-    VB_CUDA(cudaMalloc((void **)&b->d_src_orig, sizeof(int) * (size_t)std::max(n, 1)));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_src, sizeof(double) * 3 * (size_t)std::max(n, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_src_orig, sizeof(int) * (size_t)std::max(n, 1), st));
     if (n == 0) return VB200_OK;
-    DevBuf<double> d_in;
-    DevBuf<int> d_key, d_counts, d_start, d_sidx;
+    DevBuf<double> d_in(st);
+    DevBuf<int> d_key(st), d_counts(st), d_start(st), d_sidx(st);
     const size_t nb = (size_t)ncloud * kBuckets + 1;
     VB_CUDA(d_in.alloc(3 * (size_t)n));
     VB_CUDA(d_key.alloc((size_t)n));
@@ -546,11 +552,11 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
     }
     b->nblk = (int)tasks.size();
     b->ncorr_slots = corr;
-    VB_CUDA(cudaMalloc((void **)&b->d_probs, sizeof(ProbDesc) * (size_t)std::max(P, 1)));
-    VB_CUDA(cudaMalloc((void **)&b->d_states, sizeof(ProbState) * (size_t)std::max(P, 1)));
-    VB_CUDA(cudaMalloc((void **)&b->d_tasks, sizeof(BlockTask) * (size_t)std::max(b->nblk, 1)));
-    VB_CUDA(cudaMalloc((void **)&b->d_partials, sizeof(double) * kAcc * (size_t)std::max(b->nblk, 1)));
-    VB_CUDA(cudaMalloc((void **)&b->d_corr, sizeof(int) * (size_t)std::max<int64_t>(corr, 1)));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_probs, sizeof(ProbDesc) * (size_t)std::max(P, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_states, sizeof(ProbState) * (size_t)std::max(P, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_tasks, sizeof(BlockTask) * (size_t)std::max(b->nblk, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_partials, sizeof(double) * kAcc * (size_t)std::max(b->nblk, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_corr, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
     if (P) {
         VB_CUDA(cudaMemcpyAsync(b->d_probs, b->probs.data(), sizeof(ProbDesc) * (size_t)P, cudaMemcpyHostToDevice, st));
         VB_CUDA(cudaMemcpyAsync(b->d_states, states.data(), sizeof(ProbState) * (size_t)P, cudaMemcpyHostToDevice, st));

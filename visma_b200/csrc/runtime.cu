@@ -20,6 +20,13 @@ int select_device(int device) {
     }
     if (device < 0 || device >= count) return VB200_ERR_NO_DEVICE;
     VB_CUDA(cudaSetDevice(device));
+    // keep stream-ordered allocations cached in the pool between calls (see DevBuf)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
     return VB200_OK;
 }
 

@@ -224,7 +224,7 @@ class Batch:
 
 
 def RegistrationICPBatch(sources, scene, max_correspondence_distance, inits, estimation=None, criteria=None,
-                         want_corr=True):
+                         want_corr=True, packed=None):
     """open3d::RegistrationICP (Registration.h:102-107) for B independent sources through the single
     C-ABI call vb200_icp_run.  Mirrors the reference's error behaviour: on an invalid distance or missing
     normals every result is RegistrationResult(init)."""
