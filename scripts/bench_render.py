@@ -1,0 +1,35 @@
+"""BASELINE config 4 — render_depth batch: 128 chair meshes @ 640x480 on one B200, through the C ABI with host
+buffers (H2D of meshes, D2H of the float depth maps inside the timed region) and against the CPU restatement of
+the GL rules.  Run on the GPU box:  python scripts/bench_render.py > gpurun_out/render_bench.json"""
+import json, os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np
+from visma_b200 import renderer, synth
+from oracle import pyoracle
+
+V, F = synth.load_chair()
+poses = synth.render_poses(128)
+ren = renderer.Renderer(480, 640)
+ren.SetCamera(0.05, 10.0, 400.0, 400.0, 320.0, 240.0)
+ren.SetMesh(V, F)
+ren.RenderDepthBatch(list(poses))  # warm-up
+ts = []
+for _ in range(5):
+    t0 = time.perf_counter()
+    depth, z24 = ren.RenderDepthBatch(list(poses), want_z24=True)
+    ts.append(time.perf_counter() - t0)
+t = float(np.median(ts))
+# bit-exact check of 8 of the 128 maps + CPU baseline timing (the GL renderer cannot run here)
+P = pyoracle.projection(0.05, 10.0, 400.0, 400.0, 320.0, 240.0, 480, 640)
+Vw = pyoracle.view(np.eye(4, dtype=np.float32).reshape(-1))
+t0 = time.perf_counter()
+ok = True
+for i in range(0, 128, 16):
+    oz, od = pyoracle.render_depth(V, F, poses[i].T.reshape(-1), Vw, P, 480, 640)
+    ok = ok and bool((oz == z24[i]).all()) and bool((od == depth[i]).all())
+cpu_per_map = (time.perf_counter() - t0) / 8
+b_alg = 128 * (12 * len(V) + 12 * len(F) + 8 * 480 * 640)
+print(json.dumps({"maps": 128, "H": 480, "W": 640, "e2e_s_per_batch": t, "maps_per_s_e2e": 128 / t,
+                  "algorithmic_bytes": b_alg, "bit_exact_vs_oracle_8_maps": ok,
+                  "cpu_restatement_maps_per_s_1_core": 1.0 / cpu_per_map,
+                  "d2h_bytes": int(depth.nbytes + z24.nbytes)}))

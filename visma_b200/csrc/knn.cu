@@ -13,11 +13,12 @@ namespace {
 
 constexpr int kTpb = 256;
 
-__global__ void __launch_bounds__(kTpb) k_knn1(GridDev G, const double *__restrict__ q, int64_t nq, double r2,
-                                               float r2_ub, int *__restrict__ out_idx,
-                                               double *__restrict__ out_d2) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < nq;  // whole warps stay alive: the search is warp-cooperative
+__global__ void __launch_bounds__(kTpb) k_knn1(GridDev G, const double *__restrict__ q, int64_t nq,
+                                               const int *__restrict__ perm, double r2, float r2_ub,
+                                               int *__restrict__ out_idx, double *__restrict__ out_d2) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = s < nq;  // whole warps stay alive: the search is warp-cooperative
+    const int64_t i = live ? perm[s] : 0;  // queries are visited in grid order, results land in caller order
     double x = 0.0, y = 0.0, z = 0.0, d2 = 0.0;
     QueryCtx c;
     bool inside = false;
@@ -36,9 +37,13 @@ __global__ void __launch_bounds__(kTpb) k_knn1(GridDev G, const double *__restri
 int knn1_launch(Scene *sc, const double *d_q, int64_t nq, double radius, int *d_idx, double *d_d2) {
     if (!(radius > 0.0) || radius > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
     if (nq == 0) return VB200_OK;
+    if (nq > 0x7fffffff) return VB200_ERR_INVALID;
     const double r2 = (double)(float)(radius * radius);  // KDTreeFlann.cpp:185
-    k_knn1<<<div_up(nq, kTpb), kTpb, 0, sc->stream>>>(sc->grid, d_q, nq, r2, r2_upper_bound(sc->grid.p, r2),
-                                                      d_idx, d_d2);
+    DevBuf<int> d_perm(sc->stream);
+    VB_CUDA(d_perm.alloc((size_t)nq));
+    VB_TRY(grid_order_points(sc, d_q, nq, d_perm.p));
+    k_knn1<<<div_up(nq, kTpb), kTpb, 0, sc->stream>>>(sc->grid, d_q, nq, d_perm.p, r2,
+                                                      r2_upper_bound(sc->grid.p, r2), d_idx, d_d2);
     VB_CUDA(cudaGetLastError());
     return VB200_OK;
 }

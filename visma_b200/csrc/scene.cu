@@ -21,9 +21,10 @@ constexpr int kTpb = 256;
 
 __device__ __forceinline__ void fine_coords(const GridParams &g, const double *p, int &gx, int &gy, int &gz) {
     // identical expression to make_query() so build and query agree on cell membership
-    gx = (int)floor((p[0] - g.lo[0]) * g.inv_fine);
-    gy = (int)floor((p[1] - g.lo[1]) * g.inv_fine);
-    gz = (int)floor((p[2] - g.lo[2]) * g.inv_fine);
+    // fmin/fmax clamp in double first: far-away or non-finite query coordinates must not overflow the int cast
+    gx = (int)floor(fmin(fmax((p[0] - g.lo[0]) * g.inv_fine, 0.0), (double)(g.fdim[0] - 1)));
+    gy = (int)floor(fmin(fmax((p[1] - g.lo[1]) * g.inv_fine, 0.0), (double)(g.fdim[1] - 1)));
+    gz = (int)floor(fmin(fmax((p[2] - g.lo[2]) * g.inv_fine, 0.0), (double)(g.fdim[2] - 1)));
     gx = min(max(gx, 0), g.fdim[0] - 1);
     gy = min(max(gy, 0), g.fdim[1] - 1);
     gz = min(max(gz, 0), g.fdim[2] - 1);
@@ -228,6 +229,42 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     sc->grid.n = n;
     return VB200_OK;
   }
+}
+
+namespace {
+__global__ void __launch_bounds__(256) k_perm_from_keys(const unsigned long long *__restrict__ skey, int64_t n,
+                                                        int *__restrict__ perm) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) perm[s] = (int)(unsigned int)skey[s];
+}
+}  // namespace
+
+// Order arbitrary points (queries) the way the scene itself is laid out — by (coarse cell, fine cell, index)
+// of the scene's grid, points outside clamped to the border cells — so that consecutive queries are spatial
+// neighbours and the warp-cooperative search stays coherent.  d_perm[s] = index of the s-th query in that order.
+int grid_order_points(const Scene *sc, const double *d_xyz, int64_t n, int *d_perm) {
+    cudaStream_t st = sc->stream;
+    const GridParams &g = sc->grid.p;
+    const int64_t ncoarse = sc->ncoarse;
+    DevBuf<int> d_ckey(st), d_ccount(st), d_cstart(st), d_cfcount(st);
+    DevBuf<unsigned char> d_fbit(st);
+    DevBuf<unsigned long long> d_skey(st), d_cmask(st);
+    VB_CUDA(d_ckey.alloc((size_t)n));
+    VB_CUDA(d_fbit.alloc((size_t)n));
+    VB_CUDA(d_skey.alloc((size_t)n));
+    VB_CUDA(d_ccount.alloc((size_t)ncoarse + 1));
+    VB_CUDA(d_cstart.alloc((size_t)ncoarse + 1));
+    VB_CUDA(d_cfcount.alloc((size_t)ncoarse + 1));
+    VB_CUDA(d_cmask.alloc((size_t)ncoarse));
+    VB_CUDA(cudaMemsetAsync(d_ccount.p, 0, sizeof(int) * ((size_t)ncoarse + 1), st));
+    k_keys<<<div_up(n, kTpb), kTpb, 0, st>>>(g, d_xyz, n, d_ckey.p, d_fbit.p, d_ccount.p);
+    VB_TRY(exclusive_scan_i32(d_ccount.p, d_cstart.p, ncoarse + 1, nullptr, st));
+    VB_CUDA(cudaMemsetAsync(d_ccount.p, 0, sizeof(int) * ((size_t)ncoarse + 1), st));
+    k_scatter<<<div_up(n, kTpb), kTpb, 0, st>>>(d_ckey.p, d_fbit.p, n, d_cstart.p, d_ccount.p, d_skey.p);
+    k_sort_cells<<<div_up(ncoarse, 128), 128, 0, st>>>((int)ncoarse, d_cstart.p, d_skey.p, d_cmask.p, d_cfcount.p);
+    k_perm_from_keys<<<div_up(n, 256), 256, 0, st>>>(d_skey.p, n, d_perm);
+    VB_CUDA(cudaGetLastError());
+    return VB200_OK;
 }
 
 void scene_free(Scene *sc) {

@@ -17,5 +17,6 @@ struct Scene {
 
 int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, double max_radius);
 void scene_free(Scene *sc);
+int grid_order_points(const Scene *sc, const double *d_xyz, int64_t n, int *d_perm);
 
 }  // namespace vb

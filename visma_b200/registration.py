@@ -230,15 +230,23 @@ def RegistrationICPBatch(sources, scene, max_correspondence_distance, inits, est
     normals every result is RegistrationResult(init)."""
     estimation = estimation or TransformationEstimationPointToPoint()
     criteria = criteria or ICPConvergenceCriteria()
-    B = len(sources)
-    pts = [_f64(s.points_ if isinstance(s, PointCloud) else s) for s in sources]
-    # an empty source cannot "have normals" in Open3D's sense and the reference would return init for it
-    # either way; it must not switch the whole batch to the no-normals error path
-    has_n = B > 0 and all((isinstance(s, PointCloud) and s.HasNormals()) or len(p) == 0
-                          for s, p in zip(sources, pts))
-    off = np.zeros(B + 1, np.int64)
-    off[1:] = np.cumsum([len(p) for p in pts])
-    xyz = _f64(np.concatenate(pts).reshape(-1, 3)) if B else np.zeros((0, 3))
+    if packed is not None:
+        # (xyz [sum M, 3] float64 C-contiguous — e.g. a pinned buffer —, offsets [B+1], has_normals): handed
+        # to the C ABI as is, which is what a C++ caller with one contiguous allocation does
+        xyz, off, has_n = packed
+        off = np.ascontiguousarray(off, np.int64)
+        B = len(off) - 1
+        assert xyz.dtype == np.float64 and xyz.flags.c_contiguous
+    else:
+        B = len(sources)
+        pts = [_f64(s.points_ if isinstance(s, PointCloud) else s) for s in sources]
+        # an empty source cannot "have normals" in Open3D's sense and the reference would return init for it
+        # either way; it must not switch the whole batch to the no-normals error path
+        has_n = B > 0 and all((isinstance(s, PointCloud) and s.HasNormals()) or len(p) == 0
+                              for s, p in zip(sources, pts))
+        off = np.zeros(B + 1, np.int64)
+        off[1:] = np.cumsum([len(p) for p in pts])
+        xyz = _f64(np.concatenate(pts).reshape(-1, 3)) if B else np.zeros((0, 3))
     inits = _f64(np.asarray(inits).reshape(-1, 16))
     T = np.zeros((B, 4, 4))
     fit, rmse = np.zeros(B), np.zeros(B)
