@@ -149,6 +149,15 @@ int vb200_render_depth_batch(const float *V_concat, const int64_t *v_off, const 
                              const float view_T[16], float zn, float zf, float fx, float fy, float cx,
                              float cy, int H, int W, int device, uint32_t *out_z24, float *out_depth);
 
+/* Same, with two extras for pipelines that keep the maps on the GPU and for measurement: when
+ * outputs_on_device != 0, out_z24 / out_depth are DEVICE pointers written in place (no D2H copy);
+ * kernel_ms (nullable) receives the device time of the clear / rasterise / resolve launches (CUDA events). */
+int vb200_render_depth_batch_ex(const float *V_concat, const int64_t *v_off, const int32_t *F_concat,
+                                const int64_t *f_off, int32_t n_mesh, const float *model_T,
+                                const float view_T[16], float zn, float zf, float fx, float fy, float cx,
+                                float cy, int H, int W, int device, uint32_t *out_z24, float *out_depth,
+                                int outputs_on_device, float *kernel_ms);
+
 /* ---- voxel down-sample: replaces open3d::VoxelDownSample (O3D/src/Core/Geometry/DownSample.cpp:179-220),
  * the step before every ICP (src/evaluation.cpp:258, src/annotation.cpp:112).  Returns the number of
  * voxels in *out_n; out_xyz / out_nrm sized for n points (nrm/out_nrm nullable).  Output ordered by voxel

@@ -114,3 +114,14 @@ def test_full_size_properties(vb):
     dm = ((q[:, None, :] - probe[None, :, :]) ** 2).sum(-1).min(1)
     r2 = float(np.float32(0.075 * 0.075))
     assert (np.where(m, d2, r2) <= dm + 1e-15).all()
+
+
+def test_large_coherent_batch_path(vb, oracle, scene):
+    """More than 262 144 queries take the grid-ordered, warp-cooperative kernel instead of warp-per-query."""
+    tgt = scene["scene_xyz"]
+    q = np.concatenate([vb.synth.knn_queries(tgt, 280000, sigma=0.01, seed=3),
+                        vb.synth.knn_queries(tgt, 20000, sigma=0.1, seed=4)])
+    sc = vb.reg.Scene(tgt, 0.075)
+    gi, gd = sc.SearchHybrid1(q, 0.075)
+    oi, od = oracle.Index(tgt, 0.075).knn1(q, 0.075)
+    assert (gi == oi).all() and (gd == od).all()

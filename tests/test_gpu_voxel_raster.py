@@ -113,3 +113,20 @@ def test_voxel_downsample_bitexact(vb, oracle, unit_rand):
     key = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
     assert (key(g.points_) == key(pts)).all()
     assert len(vb.reg.VoxelDownSample(pts, 0.0).points_) == 0  # voxel_size <= 0 -> empty cloud
+
+
+def test_render_device_resident_outputs(vb, oracle):
+    """vb200_render_depth_batch_ex writing straight into caller-owned DEVICE buffers."""
+    torch = pytest.importorskip("torch")
+    V, F = vb.synth.load_chair()
+    poses = vb.synth.render_poses(6, seed=5)
+    r = gpu_renderer(vb)
+    r.SetMesh(V, F)
+    d_depth = torch.empty((6, 480, 640), dtype=torch.float32, device="cuda")
+    d_z = torch.empty((6, 480, 640), dtype=torch.int32, device="cuda")
+    ms = r.RenderDepthBatchDevice(list(poses), d_depth.data_ptr(), d_z.data_ptr())
+    assert ms > 0
+    for i in range(6):
+        oz, od = oracle_render(oracle, V, F, poses[i])
+        assert (d_z[i].cpu().numpy().view(np.uint32) == oz).all()
+        assert (d_depth[i].cpu().numpy() == od).all()

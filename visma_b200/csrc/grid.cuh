@@ -319,7 +319,10 @@ __device__ __forceinline__ void scan_box_uniform(const GridDev &G, const QueryCt
             }
 }
 
-constexpr int kGroupHalfWidth = 2;  // lanes within +-2 fine cells of the leader are searched together
+#ifndef VB_GROUP_HW
+#define VB_GROUP_HW 2
+#endif
+constexpr int kGroupHalfWidth = VB_GROUP_HW;  // lanes within +-2 fine cells of the leader are searched together
 
 // All 32 lanes of the warp must call this together.  `valid` = this lane has a query inside the grid.
 __device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, const QueryCtx &c, double qx, double qy,
@@ -375,6 +378,94 @@ __device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, cons
     return nn_exact_rescan(G, c, qx, qy, qz, r2, fminf(r.best + 2.0f * bb, r2_ub), d2_out);
 }
 
+// ---- warp-per-query search --------------------------------------------------------------------------------
+// For few, scattered queries (the KNN sweep: 10 000 queries in a 10 M-point scene) there is no spatial
+// coherence between lanes to exploit and too few queries to fill the GPU with one thread each.  Here the whole
+// warp serves ONE query: the cell walk is warp-uniform, the 32 lanes take consecutive candidates of a cell
+// (one coalesced 512-byte load per 32 candidates) and the per-lane best / runner-up are merged with shuffles.
+// Same decisions, same exact-double fallback, same results as the other two searches.
+__device__ __forceinline__ void wpq_merge(Screen &r) {
+    // after this every lane holds the warp-wide best (lowest position on exact f32 ties) and runner-up
+    const unsigned FULL = 0xffffffffu;
+    float best = r.best;
+    int bs = r.bs;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, o);
+        const int os = __shfl_xor_sync(FULL, bs, o);
+        const bool take = ob < best || (ob == best && (unsigned)os < (unsigned)bs);
+        best = take ? ob : best;
+        bs = take ? os : bs;
+    }
+    // runner-up: the smallest value among every lane's runner-up and every non-winning lane's best
+    float cand = (r.bs == bs) ? r.second : fminf(r.best, r.second);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cand = fminf(cand, __shfl_xor_sync(FULL, cand, o));
+    r.best = best; r.bs = bs; r.second = cand;
+}
+
+__device__ __forceinline__ void wpq_scan_run(const float4 *__restrict__ hi, int s0, int s1, const QueryCtx &c,
+                                             Screen &r) {
+    const int lane = threadIdx.x & 31;
+    for (int s = s0 + lane; s < s1; s += 32) {
+        const float4 t = __ldg(hi + s);
+        const float dx = c.qx - t.x, dy = c.qy - t.y, dz = c.qz - t.z;
+        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const bool lt = d < r.best;
+        r.second = lt ? r.best : fminf(r.second, d);
+        r.bs = lt ? s : r.bs;
+        r.best = fminf(r.best, d);
+    }
+}
+
+// All 32 lanes call with the SAME query (c, q are warp-uniform).  Returns the same value in every lane.
+__device__ __forceinline__ int nn_search_wpq(const GridDev &G, const QueryCtx &c, double qx, double qy, double qz,
+                                             double r2, float r2_ub, double *d2_out) {
+    const GridParams &g = G.p;
+    *d2_out = 0.0;
+    Screen r;  // per-lane partial state
+    r.best = r2_ub; r.second = 3.0e38f; r.bs = -1;
+    // home cell
+    {
+        const int hcx = c.gx >> 2, hcy = c.gy >> 2, hcz = c.gz >> 2;
+        const CoarseCell cc = G.coarse[((int64_t)hcz * g.cdim[1] + hcy) * g.cdim[0] + hcx];
+        const int hbit = (c.gx & 3) + 4 * (c.gy & 3) + 16 * (c.gz & 3);
+        if ((cc.mask >> hbit) & 1ull) {
+            const int rank = __popcll(cc.mask & ((1ull << hbit) - 1ull));
+            wpq_scan_run(G.hi, __ldg(G.fstart + cc.base + rank), __ldg(G.fstart + cc.base + rank + 1), c, r);
+        }
+    }
+    Screen m = r;
+    wpq_merge(m);
+    float thr = reach_of(g, m.best, r2_ub);
+    auto visit = [&](int s0, int s1, float gap2) {
+        if (gap2 > thr) return;  // warp-uniform: thr derives from the merged best
+        wpq_scan_run(G.hi, s0, s1, c, r);
+        if (s1 - s0 > 0) {
+            m = r;
+            wpq_merge(m);
+            thr = reach_of(g, m.best, r2_ub);
+        }
+    };
+    walk_cells(G, c, thr, true, visit);
+    m = r;
+    wpq_merge(m);
+    if (m.bs < 0) return -1;
+    const float bb = band(g, m.best);
+    int out;
+    double d2 = 0.0;
+    if (m.second - m.best > bb + band(g, m.second)) {
+        const double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)m.bs);
+        out = d < r2 ? m.bs : -1;
+        d2 = d < r2 ? d : 0.0;
+    } else {
+        out = nn_exact_rescan(G, c, qx, qy, qz, r2, fminf(m.best + 2.0f * bb, r2_ub), &d2);  // uniform: every lane repeats it
+    }
+    *d2_out = d2;
+    return out;
+}
+
 #endif  // __CUDACC__
+
 
 }  // namespace vb

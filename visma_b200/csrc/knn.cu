@@ -34,11 +34,36 @@ __global__ void __launch_bounds__(kTpb) k_knn1(GridDev G, const double *__restri
 }
 
 
+// one warp per query (few / scattered queries)
+__global__ void __launch_bounds__(kTpb) k_knn1_wpq(GridDev G, const double *__restrict__ q, int64_t nq, double r2,
+                                                   float r2_ub, int *__restrict__ out_idx,
+                                                   double *__restrict__ out_d2) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nq) return;  // warp-uniform exit
+    const double x = q[3 * i], y = q[3 * i + 1], z = q[3 * i + 2];
+    QueryCtx c;
+    int bs = -1;
+    double d2 = 0.0;
+    if (make_query(G.p, x, y, z, c)) bs = nn_search_wpq(G, c, x, y, z, r2, r2_ub, &d2);
+    if ((threadIdx.x & 31) == 0) {
+        out_idx[i] = bs >= 0 ? __ldg(G.orig + bs) : -1;
+        out_d2[i] = bs >= 0 ? d2 : 0.0;
+    }
+}
+
+constexpr int64_t kWarpPerQueryMax = 262144;  // below this many queries a warp per query fills the GPU better
+
 int knn1_launch(Scene *sc, const double *d_q, int64_t nq, double radius, int *d_idx, double *d_d2) {
     if (!(radius > 0.0) || radius > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
     if (nq == 0) return VB200_OK;
     if (nq > 0x7fffffff) return VB200_ERR_INVALID;
     const double r2 = (double)(float)(radius * radius);  // KDTreeFlann.cpp:185
+    if (nq <= kWarpPerQueryMax) {
+        k_knn1_wpq<<<div_up(nq * 32, kTpb), kTpb, 0, sc->stream>>>(sc->grid, d_q, nq, r2,
+                                                                   r2_upper_bound(sc->grid.p, r2), d_idx, d_d2);
+        VB_CUDA(cudaGetLastError());
+        return VB200_OK;
+    }
     DevBuf<int> d_perm(sc->stream);
     VB_CUDA(d_perm.alloc((size_t)nq));
     VB_TRY(grid_order_points(sc, d_q, nq, d_perm.p));

@@ -279,6 +279,15 @@ extern "C" int vb200_render_depth_batch(const float *V_concat, const int64_t *v_
                                         const int64_t *f_off, int32_t n_mesh, const float *model_T,
                                         const float view_T[16], float zn, float zf, float fx, float fy, float cx,
                                         float cy, int H, int W, int device, uint32_t *out_z24, float *out_depth) {
+    return vb200_render_depth_batch_ex(V_concat, v_off, F_concat, f_off, n_mesh, model_T, view_T, zn, zf, fx, fy, cx,
+                                       cy, H, W, device, out_z24, out_depth, 0, nullptr);
+}
+
+extern "C" int vb200_render_depth_batch_ex(const float *V_concat, const int64_t *v_off, const int32_t *F_concat,
+                                           const int64_t *f_off, int32_t n_mesh, const float *model_T,
+                                           const float view_T[16], float zn, float zf, float fx, float fy,
+                                           float cx, float cy, int H, int W, int device, uint32_t *out_z24,
+                                           float *out_depth, int outputs_on_device, float *kernel_ms) {
     using namespace vb;
     if (n_mesh < 0 || H <= 0 || W <= 0 || !v_off || !f_off || !view_T || (n_mesh > 0 && !model_T))
         return VB200_ERR_INVALID;
@@ -321,7 +330,7 @@ extern "C" int vb200_render_depth_batch(const float *V_concat, const int64_t *v_
     VB_CUDA(d_F.alloc(3 * (size_t)std::max<int64_t>(nf, 1)));
     VB_CUDA(d_mesh.alloc((size_t)n_mesh));
     VB_CUDA(d_tri_start.alloc((size_t)n_mesh + 1));
-    VB_CUDA(d_z.alloc((size_t)npix));
+    if (!(outputs_on_device && out_z24)) VB_CUDA(d_z.alloc((size_t)npix));
     VB_CUDA(d_big.alloc(3 * (size_t)std::max<int64_t>(nf, 1)));
     VB_CUDA(d_big_count.alloc(1));
     if (nv) VB_CUDA(cudaMemcpyAsync(d_V.p, V_concat + 3 * v_off[0], sizeof(float) * 3 * (size_t)nv, cudaMemcpyHostToDevice, st));
@@ -329,19 +338,36 @@ extern "C" int vb200_render_depth_batch(const float *V_concat, const int64_t *v_
     VB_CUDA(cudaMemcpyAsync(d_mesh.p, meshes.data(), sizeof(MeshDesc) * (size_t)n_mesh, cudaMemcpyHostToDevice, st));
     VB_CUDA(cudaMemcpyAsync(d_tri_start.p, tri_start.data(), sizeof(int) * ((size_t)n_mesh + 1), cudaMemcpyHostToDevice, st));
     VB_CUDA(cudaMemsetAsync(d_big_count.p, 0, sizeof(int), st));
-    k_clear<<<div_up(div_up(npix, 4), 256), 256, 0, st>>>(d_z.p, npix);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    struct EventGuard { cudaEvent_t &a, &b; ~EventGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } eguard{ev0, ev1};
+    if (kernel_ms) {
+        VB_CUDA(cudaEventCreate(&ev0));
+        VB_CUDA(cudaEventCreate(&ev1));
+        VB_CUDA(cudaEventRecord(ev0, st));
+    }
+    // with device outputs the kernels write straight into the caller's buffers
+    unsigned *zbuf = (outputs_on_device && out_z24) ? out_z24 : d_z.p;
+    k_clear<<<div_up(div_up(npix, 4), 256), 256, 0, st>>>(zbuf, npix);
     if (nf) {
-        k_tris<<<div_up(nf, 128), 128, 0, st>>>(d_mesh.p, d_tri_start.p, n_mesh, nf, d_V.p, d_F.p, H, W, d_z.p, d_big.p, d_big_count.p);
-        k_big<<<kNumSMsB200 * 4, 256, 0, st>>>(d_big.p, d_big_count.p, H, W, d_z.p);
+        k_tris<<<div_up(nf, 128), 128, 0, st>>>(d_mesh.p, d_tri_start.p, n_mesh, nf, d_V.p, d_F.p, H, W, zbuf, d_big.p, d_big_count.p);
+        k_big<<<kNumSMsB200 * 4, 256, 0, st>>>(d_big.p, d_big_count.p, H, W, zbuf);
     }
     VB_CUDA(cudaGetLastError());
     if (out_depth) {
-        VB_CUDA(d_depth.alloc((size_t)npix));
-        k_resolve<<<div_up(npix, 256), 256, 0, st>>>(d_z.p, d_depth.p, npix);
+        float *dd = out_depth;
+        if (!outputs_on_device) {
+            VB_CUDA(d_depth.alloc((size_t)npix));
+            dd = d_depth.p;
+        }
+        k_resolve<<<div_up(npix, 256), 256, 0, st>>>(zbuf, dd, npix);
         VB_CUDA(cudaGetLastError());
-        VB_CUDA(cudaMemcpyAsync(out_depth, d_depth.p, sizeof(float) * (size_t)npix, cudaMemcpyDeviceToHost, st));
     }
-    if (out_z24) VB_CUDA(cudaMemcpyAsync(out_z24, d_z.p, sizeof(unsigned) * (size_t)npix, cudaMemcpyDeviceToHost, st));
+    if (kernel_ms) VB_CUDA(cudaEventRecord(ev1, st));
+    if (!outputs_on_device) {
+        if (out_depth) VB_CUDA(cudaMemcpyAsync(out_depth, d_depth.p, sizeof(float) * (size_t)npix, cudaMemcpyDeviceToHost, st));
+        if (out_z24) VB_CUDA(cudaMemcpyAsync(out_z24, d_z.p, sizeof(unsigned) * (size_t)npix, cudaMemcpyDeviceToHost, st));
+    }
     VB_CUDA(cudaStreamSynchronize(st));
+    if (kernel_ms) VB_CUDA(cudaEventElapsedTime(kernel_ms, ev0, ev1));
     return VB200_OK;
 }

@@ -9,6 +9,7 @@
 #include "sort.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -197,7 +198,8 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     VB_CUDA(cudaMemcpyAsync(&nfine, d_total.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     VB_CUDA(cudaStreamSynchronize(st));
     sc->nfine = nfine;
-    if ((double)n / (double)std::max(nfine, 1) < 5.0 && attempt < 2 && n > 1000) {
+    static const double occ_target = getenv("VB200_OCC_TARGET") ? atof(getenv("VB200_OCC_TARGET")) : 5.0;  // dev knob
+    if ((double)n / (double)std::max(nfine, 1) < occ_target && attempt < 2 && n > 1000) {
         scale *= 2.0;
         continue;  // the DevBufs of this attempt are released by their destructors
     }

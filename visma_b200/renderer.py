@@ -56,6 +56,34 @@ class Renderer:
             return out
         return d
 
+    def RenderDepthBatchDevice(self, models, d_depth_ptr=None, d_z24_ptr=None, meshes=None):
+        """Device-resident form: depth maps are written to the given DEVICE pointers (n*H*W float32 /
+        uint32); returns the device time (ms) of the clear / rasterise / resolve launches."""
+        n, V, v_off, F, f_off, M = self._pack(models, meshes)
+        ms = C.c_float()
+        fp = C.POINTER(C.c_float)
+        check(lib().vb200_render_depth_batch_ex(
+            V.ctypes.data_as(fp), v_off.ctypes.data_as(C.POINTER(C.c_int64)),
+            F.ctypes.data_as(C.POINTER(C.c_int32)), f_off.ctypes.data_as(C.POINTER(C.c_int64)), n,
+            M.ctypes.data_as(fp), self.pose_.ctypes.data_as(fp), self.z_near_, self.z_far_, self.fx_, self.fy_,
+            self.cx_, self.cy_, self.rows_, self.cols_, self.device, C.c_void_p(d_z24_ptr), C.c_void_p(d_depth_ptr),
+            1, C.byref(ms)), "vb200_render_depth_batch_ex")
+        return ms.value
+
+    def _pack(self, models, meshes):
+        n = len(models)
+        if meshes is None:
+            meshes = [(self.V_, self.F_)] * n
+        Vs = [np.ascontiguousarray(np.asarray(v, np.float32).reshape(-1, 3)) for v, _ in meshes]
+        Fs = [np.ascontiguousarray(np.asarray(f, np.int32).reshape(-1, 3)) for _, f in meshes]
+        v_off = np.zeros(n + 1, np.int64); v_off[1:] = np.cumsum([len(v) for v in Vs])
+        f_off = np.zeros(n + 1, np.int64); f_off[1:] = np.cumsum([len(f) for f in Fs])
+        V = np.ascontiguousarray(np.concatenate(Vs)) if n else np.zeros((0, 3), np.float32)
+        F = np.ascontiguousarray(np.concatenate(Fs)) if n else np.zeros((0, 3), np.int32)
+        M = np.ascontiguousarray(np.stack([np.asarray(m, np.float32).reshape(4, 4).T.reshape(-1) for m in models])) \
+            if n else np.zeros((0, 16), np.float32)
+        return n, V, v_off, F, f_off, M
+
     def RenderDepthBatch(self, models, meshes=None, want_z24=False):
         """Batch form: one depth map per model pose.  meshes = optional list of (V, F), one per pose;
         default = the mesh set with SetMesh for every pose."""
