@@ -99,6 +99,8 @@ def reference_sample(d, n_obj_sample, estimator_p2plane=True):
     included, as the reference rebuilds it per call) for n_obj_sample of the 32 objects, 30 iterations each
     with the convergence test disabled so both arms do identical work.  Returns seconds."""
     from oracle import pyref
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core
+    pyref.set_num_threads(os.cpu_count() or 1)
     t0 = time.perf_counter()
     for b in range(n_obj_sample):
         src, sn = d["sources"][b]
@@ -116,6 +118,7 @@ def run_reference(args):
     if not pyref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvisma_ref.so not built"}))
         return
+    pyref.set_num_threads(os.cpu_count() or 1)
     cores = pyref.num_threads()
     d = make_workload(0)
     n_s = 1
@@ -196,6 +199,8 @@ def run_ours(args):
     ag_ms = 0.0
     if world > 1:
         out = [torch.empty_like(poses) for _ in range(world)]
+        dist.all_gather(out, poses)  # untimed: NCCL's lazy communicator set-up
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         dist.all_gather(out, poses)
