@@ -290,7 +290,9 @@ def run_ours(args):
                        "n_scene": N_SCENE, "objects_per_gpu": N_OBJ, "pts_per_object": M_PTS,
                        "l2": "256 MiB flush before every timed step (untimed)",
                        "back_to_back_ms_per_iteration_no_flush": loop_ms,
-                       "pass_ms": p_ms, "solve_ms": float(np.mean(solve_ms)), "allgather_ms": ag_ms,
+                       "pass_ms": p_ms, "pass_ms_first3": [round(float(x), 4) for x in pass_ms[:3]],
+                       "pass_ms_last3": [round(float(x), 4) for x in pass_ms[-3:]],
+                       "solve_ms": float(np.mean(solve_ms)), "allgather_ms": ag_ms,
                        "scene_build_s": scene_build_s, "converged_to_ground_truth": ok,
                        "max_pose_err_rad_m": [float(errs[:, 0].max()), float(errs[:, 1].max())]},
             "e2e": {"value": e2e_value, "unit": UNIT,

@@ -378,84 +378,6 @@ __device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, cons
     return nn_exact_rescan(G, c, qx, qy, qz, r2, fminf(r.best + 2.0f * bb, r2_ub), d2_out);
 }
 
-// ---- hybrid search: per-lane over the 27-neighbourhood, group walker for the rest ---------------------------
-// Once ICP has roughly converged a query's neighbour is a few millimetres away while a fine cell is centimetres
-// wide: the lane needs its home cell and, when it sits near a face, one or two adjacent cells — an order of
-// magnitude fewer candidates than the union box of its warp.  So each lane first scans its own home cell and the
-// neighbours its bound reaches (flat loops, per-lane addresses, L1-resident because the source clouds are sorted
-// spatially).  Lanes whose reach exceeds one fine cell — far from the surface, first iterations of a badly
-// initialised problem, empty home cell — are collected and handed to the warp-cooperative group walker above.
-// Either way every decision is re-taken in double exactly as in nn_search_warp.
-__device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, const QueryCtx &c, double qx, double qy,
-                                                double qz, double r2, float r2_ub, double *d2_out) {
-    const unsigned FULL = 0xffffffffu;
-    const GridParams &g = G.p;
-    *d2_out = 0.0;
-    Screen r;
-    r.best = r2_ub; r.second = 3.0e38f; r.bs = -1;
-    bool far = false;
-    if (valid) {
-        const int hcx = c.gx >> 2, hcy = c.gy >> 2, hcz = c.gz >> 2;
-        const CoarseCell hc = G.coarse[((int64_t)hcz * g.cdim[1] + hcy) * g.cdim[0] + hcx];
-        const int hbit = (c.gx & 3) + 4 * (c.gy & 3) + 16 * (c.gz & 3);
-        if ((hc.mask >> hbit) & 1ull) {
-            const int rank = __popcll(hc.mask & ((1ull << hbit) - 1ull));
-            scan_run(G.hi, __ldg(G.fstart + hc.base + rank), __ldg(G.fstart + hc.base + rank + 1), c, r);
-        }
-        float thr = reach_of(g, r.best, r2_ub);
-        const float inv_fine = 1.0f / g.fine;
-        const float rho = sqrtf(thr) * inv_fine * 1.001f + 1e-4f;  // reach in fine cells, padded
-        if (rho >= 1.0f) {
-            far = true;  // may need cells beyond the 27-neighbourhood
-        } else {
-            // axes along which the reach crosses the low / high face of the home cell
-            const unsigned xb = 2u | (c.fx < rho ? 1u : 0u) | (1.0f - c.fx < rho ? 4u : 0u);
-            const unsigned yb = 2u | (c.fy < rho ? 1u : 0u) | (1.0f - c.fy < rho ? 4u : 0u);
-            const unsigned zb = 2u | (c.fz < rho ? 1u : 0u) | (1.0f - c.fz < rho ? 4u : 0u);
-            const unsigned plane = ((yb & 1u) ? xb : 0u) | ((yb & 2u) ? xb << 3 : 0u) | ((yb & 4u) ? xb << 6 : 0u);
-            unsigned m = ((zb & 1u) ? plane : 0u) | ((zb & 2u) ? plane << 9 : 0u) | ((zb & 4u) ? plane << 18 : 0u);
-            m &= ~(1u << 13);  // the home cell itself
-            const float fine2 = g.fine * g.fine * 0.998f;
-            while (m) {
-                const int k = __ffs(m) - 1;
-                m &= m - 1u;
-                const int oz = k / 9, oy = (k - 9 * oz) / 3, ox = k - 9 * oz - 3 * oy;  // 0..2 each
-                const int nx = c.gx + ox - 1, ny = c.gy + oy - 1, nz = c.gz + oz - 1;
-                if ((unsigned)nx >= (unsigned)g.fdim[0] || (unsigned)ny >= (unsigned)g.fdim[1] ||
-                    (unsigned)nz >= (unsigned)g.fdim[2])
-                    continue;
-                const float ex = ox == 0 ? c.fx : (ox == 2 ? 1.0f - c.fx : 0.0f);
-                const float ey = oy == 0 ? c.fy : (oy == 2 ? 1.0f - c.fy : 0.0f);
-                const float ez = oz == 0 ? c.fz : (oz == 2 ? 1.0f - c.fz : 0.0f);
-                if ((ex * ex + ey * ey + ez * ez) * fine2 > thr) continue;  // edge / corner cell out of reach
-                const int ncx = nx >> 2, ncy = ny >> 2, ncz = nz >> 2;
-                CoarseCell cc = hc;
-                if (ncx != hcx || ncy != hcy || ncz != hcz)
-                    cc = G.coarse[((int64_t)ncz * g.cdim[1] + ncy) * g.cdim[0] + ncx];
-                const int b = (nx & 3) + 4 * (ny & 3) + 16 * (nz & 3);
-                if (!((cc.mask >> b) & 1ull)) continue;
-                const int rank = __popcll(cc.mask & ((1ull << b) - 1ull));
-                scan_run(G.hi, __ldg(G.fstart + cc.base + rank), __ldg(G.fstart + cc.base + rank + 1), c, r);
-                thr = reach_of(g, r.best, r2_ub);
-            }
-        }
-    }
-    // lanes the 27-neighbourhood could not settle: warp-cooperative walk (restarts their search)
-    if (__any_sync(FULL, far)) {
-        double d2w = 0.0;
-        const int bw = nn_search_warp(G, far, c, qx, qy, qz, r2, r2_ub, &d2w);
-        if (far) { *d2_out = d2w; return bw; }
-    }
-    if (!valid || r.bs < 0) return -1;
-    const float bb = band(g, r.best);
-    if (r.second - r.best > bb + band(g, r.second)) {
-        const double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)r.bs);
-        if (d < r2) { *d2_out = d; return r.bs; }
-        return -1;
-    }
-    return nn_exact_rescan(G, c, qx, qy, qz, r2, fminf(r.best + 2.0f * bb, r2_ub), d2_out);
-}
-
 // ---- warp-per-query search --------------------------------------------------------------------------------
 // For few, scattered queries (the KNN sweep: 10 000 queries in a 10 M-point scene) there is no spatial
 // coherence between lanes to exploit and too few queries to fill the GPU with one thread each.  Here the whole

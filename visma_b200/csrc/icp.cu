@@ -32,9 +32,6 @@ namespace vb {
 
 namespace {
 
-#ifndef VB_SEARCH_HYBRID
-#define VB_SEARCH_HYBRID 0  // 1: per-lane 27-neighbourhood search first, group walker for far lanes
-#endif
 #ifndef VB_PASS_MINBLOCKS
 #define VB_PASS_MINBLOCKS 3  // resident k_pass blocks per SM the register budget is tuned for
 #endif
@@ -172,11 +169,7 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass(GridDev G,
             inside = make_query(G.p, vs[0], vs[1], vs[2], c);
         }
         // warp-cooperative search: every lane takes part, lanes without a query just ride along
-#if VB_SEARCH_HYBRID
-        const int bs = nn_search_hybrid(G, inside, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, &d2);
-#else
         const int bs = nn_search_warp(G, inside, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, &d2);
-#endif
         matched = bs >= 0;
         if (valid) {
             int j = -1;

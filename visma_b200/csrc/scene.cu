@@ -138,7 +138,9 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     // also grown if the dense coarse array would exceed 2^27 cells.
     GridParams &g = sc->grid.p;
     double scale = 1.0;
-  for (int attempt = 0;; attempt++) {
+    const char *force = getenv("VB200_CELL_SCALE");  // dev knob: fixed scale, no adaptation
+    if (force && atof(force) >= 1.0) scale = atof(force);
+  for (int attempt = force ? 2 : 0;; attempt++) {
     double cell = max_radius * scale;
     for (;;) {
         double cells = 1.0;
