@@ -132,7 +132,7 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     for (int a = 0; a < 3; a++)
         if (!(lo[a] <= hi[a]) || !std::isfinite(lo[a]) || !std::isfinite(hi[a])) return VB200_ERR_INVALID;
 
-    // Coarse cell = scale * max radius (fine cell = 1/4 of it).  scale starts at 1 and doubles while the
+    // Coarse cell = scale * max radius (fine cell = 1/4 of it).  scale steps through 1, 1.5, 2, 3, 4 while the
     // occupied fine cells hold fewer than ~5 points on average: the search pays ~40 instructions per visited
     // cell and ~10 per candidate, so nearly-empty cells waste issue slots (measured, profiles/).  The cell is
     // also grown if the dense coarse array would exceed 2^27 cells.
@@ -140,7 +140,7 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     double scale = 1.0;
     const char *force = getenv("VB200_CELL_SCALE");  // dev knob: fixed scale, no adaptation
     if (force && atof(force) >= 1.0) scale = atof(force);
-  for (int attempt = force ? 2 : 0;; attempt++) {
+  for (int attempt = force ? 4 : 0;; attempt++) {
     double cell = max_radius * scale;
     for (;;) {
         double cells = 1.0;
@@ -201,8 +201,9 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     VB_CUDA(cudaStreamSynchronize(st));
     sc->nfine = nfine;
     static const double occ_target = getenv("VB200_OCC_TARGET") ? atof(getenv("VB200_OCC_TARGET")) : 5.0;  // dev knob
-    if ((double)n / (double)std::max(nfine, 1) < occ_target && attempt < 2 && n > 1000) {
-        scale *= 2.0;
+    if ((double)n / (double)std::max(nfine, 1) < occ_target && attempt < 4 && n > 1000) {
+        static const double kScales[5] = {1.0, 1.5, 2.0, 3.0, 4.0};  // measured optimum is flat between 1.5 and 2
+        scale = kScales[attempt + 1];
         continue;  // the DevBufs of this attempt are released by their destructors
     }
 
