@@ -158,6 +158,19 @@ int vb200_render_depth_batch_ex(const float *V_concat, const int64_t *v_off, con
                                 float cy, int H, int W, int device, uint32_t *out_z24, float *out_depth,
                                 int outputs_on_device, float *kernel_ms);
 
+/* ---- RenderEdge / RenderMask: replaces feh::Renderer::RenderEdge and RenderMask (render/renderer.cpp:353-433,
+ * render/shaders/edge_detection.frag:38-76): the depth pass above followed by the edge-detection pass on the
+ * z-buffer.  edge_z_near / edge_z_far are the edge SHADER's linearisation uniforms, which the reference fixes
+ * at 0.05 / 2.0 when it builds the shader (renderer.cpp:95-96) independently of the camera.  out_edge /
+ * out_mask: n_mesh x H x W uint8 (each nullable); edge = round(255 * soft-thresholded mean neighbour depth
+ * difference), 0 on a 5-pixel border and on background; mask = 255 where the mesh covers the pixel (the
+ * reference reads a colour buffer no shader wrote — undefined; this is the definition SURVEY §8f proposes). */
+int vb200_render_edge_mask_batch(const float *V_concat, const int64_t *v_off, const int32_t *F_concat,
+                                 const int64_t *f_off, int32_t n_mesh, const float *model_T,
+                                 const float view_T[16], float zn, float zf, float fx, float fy, float cx,
+                                 float cy, int H, int W, int device, float edge_z_near, float edge_z_far,
+                                 uint8_t *out_edge, uint8_t *out_mask, int outputs_on_device);
+
 /* ---- voxel down-sample: replaces open3d::VoxelDownSample (O3D/src/Core/Geometry/DownSample.cpp:179-220),
  * the step before every ICP (src/evaluation.cpp:258, src/annotation.cpp:112).  Returns the number of
  * voxels in *out_n; out_xyz / out_nrm sized for n points (nrm/out_nrm nullable).  Output ordered by voxel

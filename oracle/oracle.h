@@ -103,6 +103,10 @@ void vo_view(const float pose[16], float out_V[16]);
 int vo_render_depth(const float *V, int64_t nV, const int32_t *F, int64_t nF, const float model[16],
                     const float view[16], const float proj[16], int H, int W,
                     uint32_t *out_z24, float *out_depth);
+/* Renderer::RenderEdge's screen pass on a z-buffer (render/shaders/edge_detection.frag:38-76; zn/zf are the
+ * SHADER's uniforms, 0.05 / 2.0 in the reference, renderer.cpp:95-96) and RenderMask (z != 1 -> 255). */
+int vo_render_edge(const uint32_t *z24, int H, int W, float zn, float zf, uint8_t *out_edge);
+int vo_render_mask(const uint32_t *z24, int H, int W, uint8_t *out_mask);
 /* LinearizeDepth (render/renderer.h:32-36) */
 float vo_linearize_depth(float zb, float zn, float zf);
 

@@ -195,6 +195,23 @@ def render_depth(V, F, model_colmajor, view_colmajor, proj_colmajor, H, W):
     return z24, depth
 
 
+def render_edge(z24, zn=0.05, zf=2.0):
+    z24 = np.ascontiguousarray(z24, np.uint32)
+    H, W = z24.shape
+    out = np.empty((H, W), np.uint8)
+    lib().vo_render_edge(_p(z24, C.c_uint32), C.c_int(H), C.c_int(W), C.c_float(zn), C.c_float(zf),
+                         _p(out, C.c_uint8))
+    return out
+
+
+def render_mask(z24):
+    z24 = np.ascontiguousarray(z24, np.uint32)
+    H, W = z24.shape
+    out = np.empty((H, W), np.uint8)
+    lib().vo_render_mask(_p(z24, C.c_uint32), C.c_int(H), C.c_int(W), _p(out, C.c_uint8))
+    return out
+
+
 def linearize_depth(zb, zn, zf):
     return lib().vo_linearize_depth(C.c_float(zb), C.c_float(zn), C.c_float(zf))
 

@@ -206,3 +206,58 @@ int vo_render_depth(const float *V, int64_t nV, const int32_t *F, int64_t nF, co
     if (!out_z24) free(zbuf);
     return 0;
 }
+
+/* ---- RenderEdge / RenderMask (render/renderer.cpp:353-433, render/shaders/edge_detection.frag:14-76) ----
+ * RenderEdge = RenderDepth followed by a full-screen pass that linearises the depth texture with the shader's
+ * OWN z_near / z_far uniforms (fixed to 0.05 / 2.0 at construction, renderer.cpp:95-96 — not the camera's),
+ * takes the mean absolute difference of the four opposite neighbour pairs and soft-thresholds it to [0,1];
+ * a 5-texel border and background pixels are 0.  The quad maps uv (0,0) to the lower-left corner
+ * (renderer.cpp:147-153) and the colour attachment is read back as GL_UNSIGNED_BYTE (:392): unorm8 = rint(c*255).
+ * PARITY UNPINNED (vendor texture filtering / float evaluation); float ops below are evaluated left to right,
+ * unfused.  RenderMask reads a colour buffer nothing wrote (no fragment shader): undefined in the reference;
+ * defined here as 255 where the depth test passed (z != 1), else 0. */
+static float edge_linearize(uint32_t q, float zn, float zf) {
+    if (q == ZMAX24) return -1.0f;                 /* if (z == 1) return float(-1) */
+    float z = (float)((double)q / (double)ZMAX24); /* the depth texel as the sampler returns it */
+    float a = 2.0f * zn;
+    a = a * zf;
+    float b = 2.0f * z;
+    b = b - 1.0f;
+    float c = zf - zn;
+    b = b * c;
+    float d = zf + zn;
+    d = d - b;
+    return a / d;
+}
+
+int vo_render_edge(const uint32_t *z24, int H, int W, float zn, float zf, uint8_t *out_edge) {
+    const float lo = 0.05f, hi = 0.10f; /* kThreshLow / kThreshHigh */
+    for (int j = 0; j < H; j++)
+        for (int i = 0; i < W; i++) {
+            uint8_t e = 0;
+            /* pos < 5*d || pos > 1 - 5*d with pos = (i + 0.5)/W: columns 0..4 and W-5..W-1 (rows likewise) */
+            if (i >= 5 && i < W - 5 && j >= 5 && j < H - 5 && z24[(size_t)j * W + i] != ZMAX24) {
+                float v[9];
+                int k = 0;
+                for (int di = -1; di <= 1; di++)      /* value[0..8]: x outer, y inner, as in the shader */
+                    for (int dj = -1; dj <= 1; dj++) v[k++] = edge_linearize(z24[(size_t)(j + dj) * W + (i + di)], zn, zf);
+                float s = fabsf(v[1] - v[7]);
+                s = s + fabsf(v[5] - v[3]);
+                s = s + fabsf(v[0] - v[8]);
+                s = s + fabsf(v[2] - v[6]);
+                float delta = 0.25f * s;
+                float c;
+                if (delta < lo) c = 0.0f;
+                else if (delta >= hi) c = 1.0f;
+                else c = (delta - lo) / (hi - lo);
+                e = (uint8_t)lrintf(c * 255.0f);
+            }
+            out_edge[(size_t)j * W + i] = e;
+        }
+    return 0;
+}
+
+int vo_render_mask(const uint32_t *z24, int H, int W, uint8_t *out_mask) {
+    for (size_t p = 0; p < (size_t)H * W; p++) out_mask[p] = z24[p] != ZMAX24 ? 255 : 0;
+    return 0;
+}

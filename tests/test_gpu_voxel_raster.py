@@ -130,3 +130,24 @@ def test_render_device_resident_outputs(vb, oracle):
         oz, od = oracle_render(oracle, V, F, poses[i])
         assert (d_z[i].cpu().numpy().view(np.uint32) == oz).all()
         assert (d_depth[i].cpu().numpy() == od).all()
+
+
+def test_render_edge_and_mask(vb, oracle):
+    """RenderEdge / RenderMask (render/renderer.cpp:353-433, edge_detection.frag) against the restated shader."""
+    V, F = vb.synth.load_chair()
+    poses = vb.synth.render_poses(5, seed=8)
+    r = gpu_renderer(vb)
+    r.SetMesh(V, F)
+    edge, mask = r.RenderEdgeMaskBatch(list(poses))
+    for i in range(len(poses)):
+        oz, _ = oracle_render(oracle, V, F, poses[i])
+        oe, om = oracle.render_edge(oz), oracle.render_mask(oz)
+        assert (edge[i] == oe).all(), i
+        assert (mask[i] == om).all(), i
+        assert oe.max() == 255 and (oe[:5] == 0).all() and (oe[:, -5:] == 0).all()
+        assert 0 < (om == 255).sum() < om.size
+    assert (r.RenderEdge(poses[0]) == edge[0]).all() and (r.RenderMask(poses[0]) == mask[0]).all()
+    # other shader uniforms than the reference's fixed 0.05 / 2.0
+    e2, _ = r.RenderEdgeMaskBatch([poses[1]], edge_z_near=0.05, edge_z_far=10.0)
+    oz, _ = oracle_render(oracle, V, F, poses[1])
+    assert (e2[0] == oracle.render_edge(oz, 0.05, 10.0)).all()

@@ -319,50 +319,6 @@ __device__ __forceinline__ void scan_box_uniform(const GridDev &G, const QueryCt
             }
 }
 
-// Union-mask variant of the walk: every lane states the box of fine cells it needs; per coarse cell the lanes'
-// 64-bit range masks are OR-reduced across the warp (two REDUX instructions) and only the occupied cells some
-// lane asked for are scanned.  No per-cell distance test: ~45 instructions per coarse cell + ~15 per scanned
-// fine cell instead of ~40 per fine cell visited.
-template <bool EXCLUDE_HOMES>
-__device__ __forceinline__ void scan_union(const GridDev &G, const QueryCtx &cq, const QueryCtx &c, bool member,
-                                           const FineBox &need, const FineBox &wb, Screen &r) {
-    const unsigned FULL = 0xffffffffu;
-    const GridParams &g = G.p;
-    const int hcx = c.gx >> 2, hcy = c.gy >> 2, hcz = c.gz >> 2;
-    const unsigned long long hbitmask = 1ull << ((c.gx & 3) + 4 * (c.gy & 3) + 16 * (c.gz & 3));
-    for (int cz = wb.z0 >> 2; cz <= (wb.z1 >> 2); ++cz)
-        for (int cy = wb.y0 >> 2; cy <= (wb.y1 >> 2); ++cy)
-            for (int cx = wb.x0 >> 2; cx <= (wb.x1 >> 2); ++cx) {
-                const CoarseCell cc = G.coarse[((int64_t)cz * g.cdim[1] + cy) * g.cdim[0] + cx];
-                const unsigned long long m = cc.mask;
-                if (m == 0ull) continue;
-                const int ax = max(need.x0 - 4 * cx, 0), bx = min(need.x1 - 4 * cx, 3);
-                const int ay = max(need.y0 - 4 * cy, 0), by = min(need.y1 - 4 * cy, 3);
-                const int az = max(need.z0 - 4 * cz, 0), bz = min(need.z1 - 4 * cz, 3);
-                unsigned long long lm = 0ull;
-                if (member && ax <= bx && ay <= by && az <= bz) lm = range_mask(ax, bx, ay, by, az, bz);
-                unsigned long long sel =
-                        m & ((unsigned long long)__reduce_or_sync(FULL, (unsigned)lm) |
-                             ((unsigned long long)__reduce_or_sync(FULL, (unsigned)(lm >> 32)) << 32));
-                if (EXCLUDE_HOMES) {  // cells that were some member's home cell were scanned in phase 1
-                    const unsigned long long hm = (member && cx == hcx && cy == hcy && cz == hcz) ? hbitmask : 0ull;
-                    sel &= ~((unsigned long long)__reduce_or_sync(FULL, (unsigned)hm) |
-                             ((unsigned long long)__reduce_or_sync(FULL, (unsigned)(hm >> 32)) << 32));
-                }
-                while (sel) {
-                    const int b = __ffsll((long long)sel) - 1;
-                    sel &= sel - 1ull;
-                    const int rank = __popcll(m & ((1ull << b) - 1ull));
-                    const int s0 = __ldg(G.fstart + cc.base + rank), s1 = __ldg(G.fstart + cc.base + rank + 1);
-                    scan_run(G.hi, s0, s1, cq, r);
-                }
-            }
-}
-
-#ifndef VB_UNION_MASK
-#define VB_UNION_MASK 1
-#endif
-
 #ifndef VB_GROUP_HW
 #define VB_GROUP_HW 2
 #endif
@@ -396,13 +352,7 @@ __device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, cons
         b0.x0 = __reduce_min_sync(FULL, member ? c.gx : 0x7fffffff); b0.x1 = __reduce_max_sync(FULL, member ? c.gx : -0x7fffffff);
         b0.y0 = __reduce_min_sync(FULL, member ? c.gy : 0x7fffffff); b0.y1 = __reduce_max_sync(FULL, member ? c.gy : -0x7fffffff);
         b0.z0 = __reduce_min_sync(FULL, member ? c.gz : 0x7fffffff); b0.z1 = __reduce_max_sync(FULL, member ? c.gz : -0x7fffffff);
-#if VB_UNION_MASK
-        FineBox home;
-        home.x0 = home.x1 = c.gx; home.y0 = home.y1 = c.gy; home.z0 = home.z1 = c.gz;
-        scan_union<false>(G, cq, c, member, home, b0, rr);
-#else
         scan_box_uniform<false, false>(G, cq, lp, member, b0, b0, r2_ub, rr);
-#endif
         // phase 2: grow the box to cover every member's reach, skipping what phase 1 already scanned
         const float rho = sqrtf(reach_of(g, rr.best, r2_ub)) / g.fine * 1.001f + 1e-4f;
         // per-lane need: the fine cells its reach touches
@@ -416,11 +366,7 @@ __device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, cons
         b1.z0 = __reduce_min_sync(FULL, member ? need.z0 : 0x7fffffff); b1.z1 = __reduce_max_sync(FULL, member ? need.z1 : -0x7fffffff);
         b1.x0 = max(b1.x0, 0); b1.y0 = max(b1.y0, 0); b1.z0 = max(b1.z0, 0);
         b1.x1 = min(b1.x1, g.fdim[0] - 1); b1.y1 = min(b1.y1, g.fdim[1] - 1); b1.z1 = min(b1.z1, g.fdim[2] - 1);
-#if VB_UNION_MASK
-        if (!box_empty(b1)) scan_union<true>(G, cq, c, member, need, b1, rr);
-#else
         if (!box_empty(b1)) scan_box_uniform<true, true>(G, cq, lp, member, b1, b0, r2_ub, rr);
-#endif
         if (member) r = rr;
     }
     if (!valid || r.bs < 0) return -1;

@@ -240,6 +240,55 @@ __global__ void __launch_bounds__(256) k_resolve(const unsigned *__restrict__ z,
     if (i < n) depth[i] = (float)__ddiv_rn((double)z[i], (double)kZMax);
 }
 
+// Renderer::RenderEdge's full-screen pass (render/shaders/edge_detection.frag:38-76) on the integer z-buffer:
+// linearise the 3x3 neighbourhood with the SHADER's z_near/z_far (0.05 / 2.0 in the reference,
+// render/renderer.cpp:95-96), mean absolute difference of the four opposite pairs, soft threshold 0.05-0.10,
+// 5-texel border and background = 0, unorm8 output.  Float ops unfused and in the oracle's order.
+__device__ __forceinline__ float edge_linearize(unsigned q, float zn, float zf) {
+    if (q == kZMax) return -1.0f;
+    const float z = (float)__ddiv_rn((double)q, (double)kZMax);
+    float a = __fmul_rn(2.0f, zn);
+    a = __fmul_rn(a, zf);
+    float b = __fmul_rn(2.0f, z);
+    b = __fsub_rn(b, 1.0f);
+    const float c = __fsub_rn(zf, zn);
+    b = __fmul_rn(b, c);
+    float d = __fadd_rn(zf, zn);
+    d = __fsub_rn(d, b);
+    return __fdiv_rn(a, d);
+}
+
+__global__ void __launch_bounds__(256) k_edge_mask(const unsigned *__restrict__ z, int n_mesh, int H, int W, float zn,
+                                                   float zf, unsigned char *__restrict__ edge,
+                                                   unsigned char *__restrict__ mask) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (int64_t)n_mesh * H * W) return;
+    const int i = (int)(p % W), j = (int)((p / W) % H);
+    const unsigned zc = z[p];
+    if (mask) mask[p] = zc != kZMax ? 255 : 0;
+    if (!edge) return;
+    unsigned char e = 0;
+    if (i >= 5 && i < W - 5 && j >= 5 && j < H - 5 && zc != kZMax) {
+        float v[9];
+        int k = 0;
+#pragma unroll
+        for (int di = -1; di <= 1; di++)
+#pragma unroll
+            for (int dj = -1; dj <= 1; dj++) v[k++] = edge_linearize(z[p + (int64_t)dj * W + di], zn, zf);
+        float s = fabsf(__fsub_rn(v[1], v[7]));
+        s = __fadd_rn(s, fabsf(__fsub_rn(v[5], v[3])));
+        s = __fadd_rn(s, fabsf(__fsub_rn(v[0], v[8])));
+        s = __fadd_rn(s, fabsf(__fsub_rn(v[2], v[6])));
+        const float delta = __fmul_rn(0.25f, s);
+        float c;
+        if (delta < 0.05f) c = 0.0f;
+        else if (delta >= 0.10f) c = 1.0f;
+        else c = __fdiv_rn(__fsub_rn(delta, 0.05f), __fsub_rn(0.10f, 0.05f));
+        e = (unsigned char)__float2int_rn(__fmul_rn(c, 255.0f));
+    }
+    edge[p] = e;
+}
+
 // ---- host-side camera maths (float, evaluated in the order the reference / glm evaluate it) ---------
 // Renderer::SetCamera(zn, zf, intrinsics): frustum extents with top/bottom flipped (render/renderer.cpp:259-267)
 // fed to glm::frustum (RH, z in [-1,1]).
@@ -283,11 +332,37 @@ extern "C" int vb200_render_depth_batch(const float *V_concat, const int64_t *v_
                                        cy, H, W, device, out_z24, out_depth, 0, nullptr);
 }
 
+static int render_batch_impl(const float *V_concat, const int64_t *v_off, const int32_t *F_concat,
+                             const int64_t *f_off, int32_t n_mesh, const float *model_T, const float view_T[16],
+                             float zn, float zf, float fx, float fy, float cx, float cy, int H, int W, int device,
+                             uint32_t *out_z24, float *out_depth, uint8_t *out_edge, uint8_t *out_mask,
+                             float edge_zn, float edge_zf, int outputs_on_device, float *kernel_ms);
+
 extern "C" int vb200_render_depth_batch_ex(const float *V_concat, const int64_t *v_off, const int32_t *F_concat,
                                            const int64_t *f_off, int32_t n_mesh, const float *model_T,
                                            const float view_T[16], float zn, float zf, float fx, float fy,
                                            float cx, float cy, int H, int W, int device, uint32_t *out_z24,
                                            float *out_depth, int outputs_on_device, float *kernel_ms) {
+    return render_batch_impl(V_concat, v_off, F_concat, f_off, n_mesh, model_T, view_T, zn, zf, fx, fy, cx, cy, H, W,
+                             device, out_z24, out_depth, nullptr, nullptr, 0.05f, 2.0f, outputs_on_device, kernel_ms);
+}
+
+extern "C" int vb200_render_edge_mask_batch(const float *V_concat, const int64_t *v_off, const int32_t *F_concat,
+                                            const int64_t *f_off, int32_t n_mesh, const float *model_T,
+                                            const float view_T[16], float zn, float zf, float fx, float fy,
+                                            float cx, float cy, int H, int W, int device, float edge_z_near,
+                                            float edge_z_far, uint8_t *out_edge, uint8_t *out_mask,
+                                            int outputs_on_device) {
+    return render_batch_impl(V_concat, v_off, F_concat, f_off, n_mesh, model_T, view_T, zn, zf, fx, fy, cx, cy, H, W,
+                             device, nullptr, nullptr, out_edge, out_mask, edge_z_near, edge_z_far, outputs_on_device,
+                             nullptr);
+}
+
+static int render_batch_impl(const float *V_concat, const int64_t *v_off, const int32_t *F_concat,
+                             const int64_t *f_off, int32_t n_mesh, const float *model_T, const float view_T[16],
+                             float zn, float zf, float fx, float fy, float cx, float cy, int H, int W, int device,
+                             uint32_t *out_z24, float *out_depth, uint8_t *out_edge, uint8_t *out_mask,
+                             float edge_zn, float edge_zf, int outputs_on_device, float *kernel_ms) {
     using namespace vb;
     if (n_mesh < 0 || H <= 0 || W <= 0 || !v_off || !f_off || !view_T || (n_mesh > 0 && !model_T))
         return VB200_ERR_INVALID;
@@ -361,6 +436,20 @@ extern "C" int vb200_render_depth_batch_ex(const float *V_concat, const int64_t 
         }
         k_resolve<<<div_up(npix, 256), 256, 0, st>>>(zbuf, dd, npix);
         VB_CUDA(cudaGetLastError());
+    }
+    DevBuf<unsigned char> d_edge, d_mask;
+    if (out_edge || out_mask) {
+        unsigned char *de = out_edge, *dm = out_mask;
+        if (!outputs_on_device) {
+            if (out_edge) { VB_CUDA(d_edge.alloc((size_t)npix)); de = d_edge.p; }
+            if (out_mask) { VB_CUDA(d_mask.alloc((size_t)npix)); dm = d_mask.p; }
+        }
+        k_edge_mask<<<div_up(npix, 256), 256, 0, st>>>(zbuf, n_mesh, H, W, edge_zn, edge_zf, de, dm);
+        VB_CUDA(cudaGetLastError());
+        if (!outputs_on_device) {
+            if (out_edge) VB_CUDA(cudaMemcpyAsync(out_edge, d_edge.p, (size_t)npix, cudaMemcpyDeviceToHost, st));
+            if (out_mask) VB_CUDA(cudaMemcpyAsync(out_mask, d_mask.p, (size_t)npix, cudaMemcpyDeviceToHost, st));
+        }
     }
     if (kernel_ms) VB_CUDA(cudaEventRecord(ev1, st));
     if (!outputs_on_device) {

@@ -70,6 +70,29 @@ class Renderer:
             1, C.byref(ms)), "vb200_render_depth_batch_ex")
         return ms.value
 
+    def RenderEdge(self, model):
+        """RenderEdge(model) -> H x W uint8 edge map (render/renderer.cpp:353-400)."""
+        return self.RenderEdgeMaskBatch([model])[0][0]
+
+    def RenderMask(self, model):
+        """RenderMask(model) -> H x W uint8, 255 where the mesh covers the pixel (render/renderer.cpp:403-433)."""
+        return self.RenderEdgeMaskBatch([model])[1][0]
+
+    def RenderEdgeMaskBatch(self, models, meshes=None, edge_z_near=0.05, edge_z_far=2.0):
+        """(edge, mask), each n x H x W uint8.  edge_z_near / edge_z_far default to the values the reference
+        hard-wires into its edge shader (render/renderer.cpp:95-96)."""
+        n, V, v_off, F, f_off, M = self._pack(models, meshes)
+        edge = np.empty((n, self.rows_, self.cols_), np.uint8)
+        mask = np.empty((n, self.rows_, self.cols_), np.uint8)
+        fp = C.POINTER(C.c_float)
+        check(lib().vb200_render_edge_mask_batch(
+            V.ctypes.data_as(fp), v_off.ctypes.data_as(C.POINTER(C.c_int64)),
+            F.ctypes.data_as(C.POINTER(C.c_int32)), f_off.ctypes.data_as(C.POINTER(C.c_int64)), n,
+            M.ctypes.data_as(fp), self.pose_.ctypes.data_as(fp), self.z_near_, self.z_far_, self.fx_, self.fy_,
+            self.cx_, self.cy_, self.rows_, self.cols_, self.device, edge_z_near, edge_z_far,
+            edge.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p), 0), "vb200_render_edge_mask_batch")
+        return edge, mask
+
     def _pack(self, models, meshes):
         n = len(models)
         if meshes is None:
