@@ -32,10 +32,14 @@ namespace vb {
 
 namespace {
 
-#ifndef VB_PASS_MINBLOCKS
-#define VB_PASS_MINBLOCKS 3  // resident k_pass blocks per SM the register budget is tuned for
+#ifndef VB_PASS_TPB
+#define VB_PASS_TPB 128
 #endif
-constexpr int kPassTpb = 256;
+#ifndef VB_PASS_MINBLOCKS
+#define VB_PASS_MINBLOCKS (768 / VB_PASS_TPB)  // 24 resident warps per SM -> 80 registers per thread
+#endif
+constexpr int kPassTpb = VB_PASS_TPB;
+constexpr int kPassWarps = kPassTpb / 32;  // every warp writes its own partial: no block-level barrier
 constexpr int kPtsPerThread = 4;
 constexpr int kChunk = kPassTpb * kPtsPerThread;  // source points per block
 constexpr int kAcc = 32;                          // accumulator slots (padded)
@@ -141,20 +145,17 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass(GridDev G,
     const BlockTask task = tasks[blockIdx.x];
     const ProbState *st = states + task.prob;
     if (st->done) return;
-    __shared__ double sT[12];
-    __shared__ double swarp[kPassTpb / 32][kAcc];
-    if (threadIdx.x < 12) sT[threadIdx.x] = st->T[threadIdx.x];
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double T[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) T[i] = sT[i];
+    for (int i = 0; i < 12; i++) T[i] = st->T[i];  // warp-uniform broadcast loads
     // cref = translation part of T: keeps the p2p moments O(object size) instead of O(scene size)
     const double cref[3] = {T[3], T[7], T[11]};
     double acc = 0.0;  // lane L accumulates slot L
 #pragma unroll 1
     for (int k = 0; k < kPtsPerThread; k++) {
-        const int local = k * kPassTpb + threadIdx.x;
+        // a warp owns kPtsPerThread consecutive batches of 32 consecutive (spatially sorted) points
+        const int local = (warp * kPtsPerThread + k) * 32 + lane;
         const bool valid = local < task.count;
         bool matched = false;
         double d2 = 0.0, vs[3] = {0, 0, 0}, vt[3] = {0, 0, 0}, nt[3] = {0, 0, 0};
@@ -188,14 +189,7 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass(GridDev G,
         contributions<MODE>(matched, d2, vs, vt, nt, cref, v);
         acc += warp_reduce_slots(v);
     }
-    swarp[warp][lane] = acc;
-    __syncthreads();
-    if (threadIdx.x < kAcc) {
-        double s = swarp[0][threadIdx.x];
-#pragma unroll
-        for (int w = 1; w < kPassTpb / 32; w++) s += swarp[w][threadIdx.x];
-        partials[(int64_t)blockIdx.x * kAcc + threadIdx.x] = s;
-    }
+    partials[((int64_t)blockIdx.x * kPassWarps + warp) * kAcc + lane] = acc;  // one coalesced 256-byte row per warp
 }
 
 // ---- estimator solves from the reduced slots ---------------------------------------------------------
@@ -257,7 +251,8 @@ __global__ void __launch_bounds__(256) k_solve(const ProbDesc *__restrict__ prob
     __shared__ double tot[kAcc];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double s = 0.0;
-    for (int b = warp; b < pd.blk_count; b += 8) s += partials[(int64_t)(pd.blk_begin + b) * kAcc + lane];
+    for (int b = warp; b < pd.blk_count * kPassWarps; b += 8)
+        s += partials[((int64_t)pd.blk_begin * kPassWarps + b) * kAcc + lane];
     sw[warp][lane] = s;
     __syncthreads();
     if (threadIdx.x < kAcc) {
@@ -555,7 +550,7 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
     VB_CUDA(cudaMallocAsync((void **)&b->d_probs, sizeof(ProbDesc) * (size_t)std::max(P, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_states, sizeof(ProbState) * (size_t)std::max(P, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_tasks, sizeof(BlockTask) * (size_t)std::max(b->nblk, 1), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_partials, sizeof(double) * kAcc * (size_t)std::max(b->nblk, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_partials, sizeof(double) * kAcc * kPassWarps * (size_t)std::max(b->nblk, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_corr, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
     if (P) {
         VB_CUDA(cudaMemcpyAsync(b->d_probs, b->probs.data(), sizeof(ProbDesc) * (size_t)P, cudaMemcpyHostToDevice, st));
