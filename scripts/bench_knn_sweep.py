@@ -19,7 +19,8 @@ Q, R = 10_000, 0.075
 dev = torch.device("cuda", 0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 rows = []
-for N in (100_000, 300_000, 1_000_000, 3_000_000, 10_000_000):
+SIZES = [int(float(a)) for a in sys.argv[1:]] or [100_000, 300_000, 1_000_000, 3_000_000, 10_000_000]
+for N in SIZES:
     d = synth.make_room_scene(N, 8, 10)
     t0 = time.perf_counter()
     scene = reg.Scene(reg.PointCloud(d["scene_xyz"], d["scene_nrm"]), R)
