@@ -45,6 +45,16 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_pass launch from the latest committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)["k_pass"]
+        return int(t["dram_bytes_read"] + t["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(n_scene, m_total, k_total, n_obj):
     """16N [scene once] + sum(16 M + 8 M) [source in, corr out] + sum K (8 + 16 + 16 + 16)
     [corr in, src, target point, target normal] + 27*8 per object [JTJ/JTr out]."""
@@ -302,7 +312,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "k_pass<point-to-plane>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(), "peak_source": how,
                          "algorithmic_bytes": b_alg},
             "cpu_baseline": cpu,
         }

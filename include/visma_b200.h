@@ -178,6 +178,15 @@ int vb200_render_edge_mask_batch(const float *V_concat, const int64_t *v_off, co
 int vb200_voxel_downsample(const double *xyz, const double *nrm, int64_t n, double voxel_size, int device,
                            double *out_xyz, double *out_nrm, int64_t *out_n);
 
+/* ---- mesh surface sampling: replaces feh::SamplePointCloudFromMesh (include/geometry.h:29-64), which builds
+ * every ICP source cloud (src/evaluation.cpp:250-256, src/annotation.cpp:126).  V: nV x 3 float, F: nF x 3
+ * int32; writes exactly n_samples area-weighted surface points (double xyz) and, if out_nrm is non-null, the
+ * unit face normal of each sample.  Reproducible from `seed` (counter-based Philox keyed by sample index).
+ * The reference seeds from the wall clock, mis-indexes the chosen face by one and samples the triangle's
+ * parallelogram; neither quirk is reproduced (see sample.cu), so parity is statistical. */
+int vb200_sample_mesh(const float *V, int64_t nV, const int32_t *F, int64_t nF, int64_t n_samples,
+                      uint64_t seed, int device, double *out_xyz, double *out_nrm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -225,3 +225,50 @@ def voxel_downsample(xyz, voxel, nrm=None):
     if k < 0:
         raise ValueError("vo_voxel_downsample rc=%d" % k)
     return (out[:k], out_n[:k]) if nrm is not None else out[:k]
+
+
+# ---- mesh surface sampling ---------------------------------------------------------------------------------
+def _philox4x32_10(c0, c1, k0, k1):
+    """Philox4x32-10 on numpy uint32 arrays (counter words c0, c1; c2 = c3 = 0), vectorised."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+    c0 = c0.astype(np.uint32); c1 = c1.astype(np.uint32)
+    c2 = np.zeros_like(c0); c3 = np.zeros_like(c0)
+    k0 = np.full_like(c0, k0); k1 = np.full_like(c0, k1)
+    for _ in range(10):
+        p0 = M0 * c0.astype(np.uint64)
+        p1 = M1 * c2.astype(np.uint64)
+        n0 = (p1 >> np.uint64(32)).astype(np.uint32) ^ c1 ^ k0
+        n1 = (p1 & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        n2 = (p0 >> np.uint64(32)).astype(np.uint32) ^ c3 ^ k1
+        n3 = (p0 & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        with np.errstate(over="ignore"):
+            k0 = k0 + W0
+            k1 = k1 + W1
+    return c0, c1, c2, c3
+
+
+def sample_mesh(V, F, n, seed=0):
+    """Seeded restatement of feh::SamplePointCloudFromMesh (include/geometry.h:29-64) with the reference's two
+    defects repaired (face index off by one, parallelogram instead of triangle) — the algorithm
+    vb200_sample_mesh implements.  PARITY WITH THE REFERENCE IS STATISTICAL ONLY: it seeds from the wall clock
+    (geometry.h:47).  Returns (points, unit face normals, face index)."""
+    V = np.asarray(V, np.float32).astype(np.float64)
+    F = np.asarray(F, np.int64)
+    v0, e1, e2 = V[F[:, 0]], V[F[:, 1]] - V[F[:, 0]], V[F[:, 2]] - V[F[:, 0]]
+    cr = np.cross(e1, e2)
+    area = 0.5 * np.sqrt((cr[:, 0] * cr[:, 0] + cr[:, 1] * cr[:, 1]) + cr[:, 2] * cr[:, 2])
+    cdf = np.cumsum(area)  # sequential double sum, as geometry.h:41-44
+    i = np.arange(n, dtype=np.uint64)
+    r0, r1, r2, r3 = _philox4x32_10((i & np.uint64(0xFFFFFFFF)).astype(np.uint32), (i >> np.uint64(32)).astype(np.uint32),
+                                    np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF))
+    r = (r0.astype(np.float64) * 4294967296.0 + r1.astype(np.float64)) * (1.0 / 18446744073709551616.0) * cdf[-1]
+    f = np.searchsorted(cdf, r, side="right").clip(0, len(F) - 1)
+    a = r2.astype(np.float64) * (1.0 / 4294967296.0)
+    b = r3.astype(np.float64) * (1.0 / 4294967296.0)
+    fold = a + b > 1.0
+    a = np.where(fold, 1.0 - a, a)
+    b = np.where(fold, 1.0 - b, b)
+    pts = (v0[f] + a[:, None] * e1[f]) + b[:, None] * e2[f]
+    nr = cr[f] / np.maximum(np.linalg.norm(cr[f], axis=1, keepdims=True), 1e-300)
+    return pts, nr, f

@@ -130,3 +130,10 @@ def test_gravity_estimator_properties(oracle):
     r = lambda th: np.einsum("ij,ij->i", vs @ rot_y(th).T - vt, nt)
     fd = (r(eps) - r(-eps)) / (2 * eps)
     assert np.allclose(fd, np.cross(vs, nt)[:, 1], atol=1e-6)
+
+
+def test_unorm24_to_float_identity():
+    """raster.cu turns q / (2^24-1) into a double multiply by the rounded reciprocal; the float result must be
+    that of the exact division (what the oracle computes) for EVERY 24-bit depth value."""
+    q = np.arange(0, 1 << 24, dtype=np.float64)
+    assert ((q / 16777215.0).astype(np.float32) == (q * (1.0 / 16777215.0)).astype(np.float32)).all()

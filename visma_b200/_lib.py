@@ -21,7 +21,7 @@ SYMBOLS = [
     "vb200_scene_sync", "vb200_knn1", "vb200_knn1_device", "vb200_icp_run", "vb200_batch_create",
     "vb200_batch_destroy", "vb200_batch_set_problems", "vb200_batch_run", "vb200_batch_results",
     "vb200_batch_corr", "vb200_batch_launches", "vb200_batch_iterate", "vb200_batch_last_kernel_ms", "vb200_estimate", "vb200_register_model_to_scene",
-    "vb200_render_depth_batch", "vb200_render_depth_batch_ex", "vb200_render_edge_mask_batch", "vb200_voxel_downsample",
+    "vb200_render_depth_batch", "vb200_render_depth_batch_ex", "vb200_render_edge_mask_batch", "vb200_voxel_downsample", "vb200_sample_mesh",
 ]
 
 
@@ -91,6 +91,7 @@ def lib():
                                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                                C.c_int, C.c_float, C.c_float, vp, vp, C.c_int]
     L.vb200_voxel_downsample.argtypes = [dp, dp, C.c_int64, C.c_double, C.c_int, dp, dp, i64p]
+    L.vb200_sample_mesh.argtypes = [fp, C.c_int64, ip, C.c_int64, C.c_int64, C.c_uint64, C.c_int, dp, dp]
     _lib = L
     return L
 

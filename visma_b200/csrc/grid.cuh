@@ -97,6 +97,9 @@ __device__ __forceinline__ bool make_query(const GridParams &g, double x, double
     return true;
 }
 
+// small non-negative int -> float without the (quarter-rate) I2F conversion unit
+__device__ __forceinline__ float small_int_to_float(int v) { return __int_as_float(0x4B000000 | v) - 8388608.0f; }
+
 // squared distance (fine-cell units) from the query to fine cell at integer offset o along one axis
 __device__ __forceinline__ float axis_gap(int o, float frac) {
     float a = o > 0 ? (float)o - frac : (o < 0 ? frac - (float)(o + 1) : 0.0f);
@@ -136,7 +139,16 @@ __device__ __forceinline__ void scan_run(const float4 *__restrict__ hi, int s0, 
         const float4 t0 = __ldg(hi + s), t1 = __ldg(hi + s + 1), t2 = __ldg(hi + s + 2), t3 = __ldg(hi + s + 3);
         consider(t0, s); consider(t1, s + 1); consider(t2, s + 2); consider(t3, s + 3);
     }
-    for (; s < s1; ++s) consider(__ldg(hi + s), s);
+    const int rem = s1 - s;  // 0..3 left: issue their loads together, no loop
+    if (rem > 0) {
+        const float4 t0 = __ldg(hi + s);
+        float4 t1 = t0, t2 = t0;
+        if (rem > 1) t1 = __ldg(hi + s + 1);
+        if (rem > 2) t2 = __ldg(hi + s + 2);
+        consider(t0, s);
+        if (rem > 1) consider(t1, s + 1);
+        if (rem > 2) consider(t2, s + 2);
+    }
 }
 
 template <class Visit>
@@ -168,14 +180,21 @@ __device__ __forceinline__ void walk_cells(const GridDev &G, const QueryCtx &c, 
                 int az = max(fz0 - 4 * cz, 0), bz = min(fz1 - 4 * cz, 3);
                 unsigned long long sel = m & range_mask(ax, bx, ay, by, az, bz);
                 if (skip_home && cx == hcx && cy == hcy && cz == hcz) sel &= ~(1ull << hbit);
+                if (sel == 0ull) continue;
+                // query position relative to this coarse cell's corner, in fine-cell units (conversions once
+                // per coarse cell; the per-fine-cell offsets below avoid the quarter-rate I2F unit)
+                const float rx = (float)(c.gx - 4 * cx) + c.fx, ry = (float)(c.gy - 4 * cy) + c.fy,
+                            rz = (float)(c.gz - 4 * cz) + c.fz;
                 while (sel) {
                     int b = __ffsll((long long)sel) - 1;
                     sel &= sel - 1ull;
-                    int ox = 4 * cx + (b & 3) - c.gx, oy = 4 * cy + ((b >> 2) & 3) - c.gy,
-                        oz = 4 * cz + (b >> 4) - c.gz;
-                    float gx = axis_gap(ox, c.fx), gy = axis_gap(oy, c.fy), gz = axis_gap(oz, c.fz);
+                    const float fx = small_int_to_float(b & 3), fy = small_int_to_float((b >> 2) & 3),
+                                fz = small_int_to_float(b >> 4);
+                    const float gx = fmaxf(fmaxf(fx - rx, rx - fx - 1.0f), 0.0f);
+                    const float gy = fmaxf(fmaxf(fy - ry, ry - fy - 1.0f), 0.0f);
+                    const float gz = fmaxf(fmaxf(fz - rz, rz - fz - 1.0f), 0.0f);
                     // lower bound of the squared distance to anything in that cell (metric), deflated
-                    float gap2 = (gx * gx + gy * gy + gz * gz) * fine2 * 0.9999f - 1e-12f * fine2;
+                    float gap2 = (gx * gx + gy * gy + gz * gz) * fine2 * 0.998f - 1e-12f * fine2;
                     int rank = __popcll(m & ((1ull << b) - 1ull));
                     int s0 = __ldg(G.fstart + cc.base + rank), s1 = __ldg(G.fstart + cc.base + rank + 1);
                     visit(s0, s1, gap2);
@@ -259,8 +278,6 @@ struct FineBox { int x0, x1, y0, y1, z0, z1; };
 
 __device__ __forceinline__ bool box_empty(const FineBox &b) { return b.x0 > b.x1 || b.y0 > b.y1 || b.z0 > b.z1; }
 
-// small non-negative int -> float without the (quarter-rate) I2F conversion unit
-__device__ __forceinline__ float small_int_to_float(int v) { return __int_as_float(0x4B000000 | v) - 8388608.0f; }
 
 // upper bound of best + 2*band(best), capped at the acceptance bound (fast reciprocal sqrt, padded)
 __device__ __forceinline__ float reach_of(const GridParams &g, float best, float r2_ub) {

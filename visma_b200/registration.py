@@ -323,3 +323,15 @@ def VoxelDownSample(cloud, voxel_size, device=0):
         return PointCloud(np.zeros((0, 3)))  # reference returns an empty cloud
     check(rc, "vb200_voxel_downsample")
     return PointCloud(out[:k.value].copy(), None if out_n is None else out_n[:k.value].copy())
+
+
+def SamplePointCloudFromMesh(V, F, max_num_pts=1000, seed=0, device=0, with_normals=False):
+    """feh::SamplePointCloudFromMesh (include/geometry.h:29-64) on the GPU: area-weighted surface samples,
+    reproducible from `seed`.  Returns points (and unit face normals when asked)."""
+    V = np.ascontiguousarray(np.asarray(V, np.float32).reshape(-1, 3))
+    F = np.ascontiguousarray(np.asarray(F, np.int32).reshape(-1, 3))
+    out = np.empty((int(max_num_pts), 3), np.float64)
+    nrm = np.empty((int(max_num_pts), 3), np.float64) if with_normals else None
+    check(lib().vb200_sample_mesh(V.ctypes.data_as(C.POINTER(C.c_float)), len(V), _ip(F), len(F), int(max_num_pts),
+                                  int(seed), device, _dp(out), _dp(nrm)), "vb200_sample_mesh")
+    return (out, nrm) if with_normals else out
