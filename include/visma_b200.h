@@ -120,6 +120,24 @@ int vb200_batch_iterate(vb200_batch_t *batch, int estimator, const double *gravi
  * the solve kernel launches issued by the most recent vb200_batch_iterate call; synchronises. */
 int vb200_batch_last_kernel_ms(vb200_batch_t *batch, float *pass_ms, float *solve_ms);
 
+/* ---- one cloud sharded over several GPUs (ICPRefinement's single global transform, src/evaluation.cpp:
+ * 244-274, at multi-GPU scale): an iteration split at the only point where ranks must exchange data.
+ *   vb200_batch_pass    correspondence pass over THIS rank's shard + per-problem totals (P x 32 doubles:
+ *                       the 27 normal-equation sums or the 16 moments, sum d2, count) left in device memory;
+ *   (caller)            all-reduce (sum) of the totals buffer across ranks — e.g. ncclAllReduce, 256 B/problem;
+ *   vb200_batch_solve   fitness / rmse / convergence test / estimator update from the combined totals.
+ * Every rank sees identical totals and therefore applies the identical update: transforms stay consistent
+ * without a broadcast.  npts_global[P] (nullable = local sizes): source points of each problem over ALL ranks
+ * (the fitness denominator, Registration.cpp:91).  pass_index: 0 for the pass at the initial transform, then
+ * 1, 2, ... ; iteration k's update is skipped once pass_index >= max_iter or the problem has converged.
+ * vb200_batch_set_totals_buffer lets the caller own the totals buffer (e.g. a torch tensor handed to NCCL). */
+int vb200_batch_pass(vb200_batch_t *batch, int estimator, double max_dist);
+int vb200_batch_set_totals_buffer(vb200_batch_t *batch, void *d_totals);
+void *vb200_batch_totals(vb200_batch_t *batch);
+int vb200_batch_solve(vb200_batch_t *batch, int estimator, const double *gravity_axis, double max_dist,
+                      double rel_fitness, double rel_rmse, int max_iter, int pass_index,
+                      const int64_t *npts_global);
+
 /* ---- estimator plug-in: replaces TransformationEstimation::ComputeTransformation(source, target,
  * corres) (O3D/src/Core/Registration/TransformationEstimation.h:51-66; VISMA's subclass
  * include/constrained_ICP.h:22-26), so the reference's own CPU ICP loop can drive the GPU estimator.

@@ -223,3 +223,45 @@ def test_full_size_workload(vb, oracle):
         rot, tr = vb.synth.pose_error(res[b].transformation_, o["T"])
         assert rot < ROT_TOL and tr < TRANS_TOL and rot < 1e-6 and tr < 1e-6, (b, rot, tr)
         assert abs(res[b].fitness_ - o["fitness"]) <= 2.0 / 50_000
+
+
+@pytest.mark.parametrize("name", ["p2p", "p2plane"])
+def test_split_iteration_equals_fused(vb, scene, name):
+    """vb200_batch_pass / (sum of totals) / vb200_batch_solve — the iteration split at the cross-GPU exchange
+    point — on two shards of one cloud must reproduce the single-batch RegistrationICP of the whole cloud."""
+    torch = pytest.importorskip("torch")
+    est = (vb.reg.TransformationEstimationPointToPoint() if name == "p2p"
+           else vb.reg.TransformationEstimationPointToPlane())
+    sc = vb.reg.Scene(vb.reg.PointCloud(scene["scene_xyz"], scene["scene_nrm"]), 0.075)
+    src, sn = scene["sources"][0]
+    init = scene["T_init"][0]
+    crit = vb.reg.ICPConvergenceCriteria()
+    whole = vb.reg.RegistrationICP(vb.reg.PointCloud(src, sn), sc, 0.075, init, est, crit)
+    cut = 2500
+    shards = [vb.reg.PointCloud(src[:cut], sn[:cut]), vb.reg.PointCloud(src[cut:], sn[cut:])]
+    batches, totals = [], []
+    for sh in shards:
+        b = vb.reg.Batch(sc, [sh])
+        b.set_problems(init.reshape(1, 16))
+        t = torch.zeros(32, dtype=torch.float64, device="cuda")
+        b.set_totals_buffer(t.data_ptr())
+        batches.append(b)
+        totals.append(t)
+    for it in range(crit.max_iteration_ + 1):
+        for b in batches:
+            b.pass_(est, 0.075)
+        sc.sync()
+        tot = totals[0] + totals[1]          # what the all-reduce produces on every rank
+        torch.cuda.synchronize()
+        for t in totals:
+            t.copy_(tot)
+        torch.cuda.synchronize()
+        for b in batches:
+            b.solve(est, 0.075, crit, it, [len(src)])
+    ra, rb = batches[0].results()[0], batches[1].results()[0]
+    assert np.array_equal(ra.transformation_, rb.transformation_)  # ranks stay consistent without a broadcast
+    assert ra.fitness_ == rb.fitness_ and ra.iterations_ == rb.iterations_
+    rot, tr = vb.synth.pose_error(ra.transformation_, whole.transformation_)
+    assert rot < 1e-9 and tr < 1e-9
+    assert abs(ra.fitness_ - whole.fitness_) <= 1.0 / len(src) and abs(ra.inlier_rmse_ - whole.inlier_rmse_) < 1e-9
+    assert ra.iterations_ == whole.iterations_

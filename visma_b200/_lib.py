@@ -20,7 +20,8 @@ SYMBOLS = [
     "vb200_scene_create", "vb200_scene_destroy", "vb200_scene_size", "vb200_scene_stream",
     "vb200_scene_sync", "vb200_knn1", "vb200_knn1_device", "vb200_icp_run", "vb200_batch_create",
     "vb200_batch_destroy", "vb200_batch_set_problems", "vb200_batch_run", "vb200_batch_results",
-    "vb200_batch_corr", "vb200_batch_launches", "vb200_batch_iterate", "vb200_batch_last_kernel_ms", "vb200_estimate", "vb200_register_model_to_scene",
+    "vb200_batch_corr", "vb200_batch_launches", "vb200_batch_iterate", "vb200_batch_last_kernel_ms", "vb200_batch_pass",
+    "vb200_batch_set_totals_buffer", "vb200_batch_totals", "vb200_batch_solve", "vb200_estimate", "vb200_register_model_to_scene",
     "vb200_render_depth_batch", "vb200_render_depth_batch_ex", "vb200_render_edge_mask_batch", "vb200_voxel_downsample", "vb200_sample_mesh",
 ]
 
@@ -79,6 +80,11 @@ def lib():
     L.vb200_batch_launches.argtypes = [vp]
     L.vb200_batch_iterate.argtypes = [vp, C.c_int, dp, C.c_double, C.c_int]
     L.vb200_batch_last_kernel_ms.argtypes = [vp, fp, fp]
+    L.vb200_batch_pass.argtypes = [vp, C.c_int, C.c_double]
+    L.vb200_batch_set_totals_buffer.argtypes = [vp, vp]
+    L.vb200_batch_totals.restype = vp
+    L.vb200_batch_totals.argtypes = [vp]
+    L.vb200_batch_solve.argtypes = [vp, C.c_int, dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, i64p]
     L.vb200_estimate.argtypes = [dp, C.c_int64, dp, dp, C.c_int64, ip, C.c_int64, C.c_int, dp, C.c_int, dp]
     L.vb200_register_model_to_scene.argtypes = [vp, dp, dp, C.c_int64, C.c_int, C.c_double, C.c_int, dp, ip, ip]
     L.vb200_render_depth_batch.argtypes = [fp, i64p, ip, i64p, C.c_int32, fp, fp, C.c_float, C.c_float,

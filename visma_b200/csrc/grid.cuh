@@ -134,10 +134,24 @@ __device__ __forceinline__ void scan_run(const float4 *__restrict__ hi, int s0, 
         r.bs = lt ? s : r.bs;
         r.best = fminf(r.best, d);
     };
+    // two candidates are ordered against each other first (independent of the running state), then merged:
+    // the dependent chain through best / second / bs is one merge per pair instead of one per candidate
+    auto consider2 = [&](const float4 ta, const float4 tb, int s) {
+        const float ax = c.qx - ta.x, ay = c.qy - ta.y, az = c.qz - ta.z;
+        const float bx = c.qx - tb.x, by = c.qy - tb.y, bz = c.qz - tb.z;
+        const float da = fmaf(az, az, fmaf(ay, ay, ax * ax)), db = fmaf(bz, bz, fmaf(by, by, bx * bx));
+        const float lo = fminf(da, db), hi2 = fmaxf(da, db);
+        const int slo = db < da ? s + 1 : s;
+        const bool lt = lo < r.best;
+        r.second = fminf(fminf(r.second, hi2), fmaxf(lo, r.best));  // ties (lo == best, da == db) stay visible
+        r.bs = lt ? slo : r.bs;
+        r.best = fminf(r.best, lo);
+    };
     int s = s0;
     for (; s + 3 < s1; s += 4) {  // four independent 16-byte loads in flight per iteration
         const float4 t0 = __ldg(hi + s), t1 = __ldg(hi + s + 1), t2 = __ldg(hi + s + 2), t3 = __ldg(hi + s + 3);
-        consider(t0, s); consider(t1, s + 1); consider(t2, s + 2); consider(t3, s + 3);
+        consider2(t0, t1, s);
+        consider2(t2, t3, s + 2);
     }
     const int rem = s1 - s;  // 0..3 left: issue their loads together, no loop
     if (rem > 0) {

@@ -241,14 +241,9 @@ __device__ void update_p2p(const double *tot, const double *cref, double *U) {
 
 // One block per problem: fixed-order reduction of the pass partials, result bookkeeping, convergence test
 // (Registration.cpp:179-183) and the estimator update T <- update * T (Registration.cpp:172-174).
-__global__ void __launch_bounds__(256) k_solve(const ProbDesc *__restrict__ probs, ProbState *__restrict__ states,
-                                               const double *__restrict__ partials, SolveParams sp,
-                                               int pass_index) {
-    const ProbDesc pd = probs[blockIdx.x];
-    ProbState *st = states + blockIdx.x;
-    if (st->done) return;
-    __shared__ double sw[8][kAcc];
-    __shared__ double tot[kAcc];
+// fixed-order reduction of one problem's per-warp partials into tot[kAcc] (shared memory); 256 threads
+__device__ __forceinline__ void reduce_partials(const ProbDesc &pd, const double *__restrict__ partials,
+                                                double (*sw)[kAcc], double *tot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double s = 0.0;
     for (int b = warp; b < pd.blk_count * kPassWarps; b += 8)
@@ -261,11 +256,15 @@ __global__ void __launch_bounds__(256) k_solve(const ProbDesc *__restrict__ prob
         tot[threadIdx.x] = t;
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
+}
+
+// result bookkeeping (Registration.cpp:87-93), convergence test (:179-183) and estimator update (:172-174)
+// from the reduced slots; one thread.  npts = source points the totals were accumulated over.
+__device__ void solve_from_totals(const double *tot, double npts, ProbState *st, const SolveParams &sp, int pass_index) {
     const double K = tot[kSlotCount];
     double fitness = 0.0, rmse = 0.0;
-    if (K > 0.0 && pd.npts > 0) {  // Registration.cpp:87-93
-        fitness = K / (double)pd.npts;
+    if (K > 0.0 && npts > 0.0) {
+        fitness = K / npts;
         rmse = sqrt(tot[kSlotD2] / K);
     }
     st->fitness = fitness;
@@ -293,6 +292,46 @@ __global__ void __launch_bounds__(256) k_solve(const ProbDesc *__restrict__ prob
     mat4_mul(U, T, T);
     for (int i = 0; i < 16; i++) st->T[i] = T[i];
     st->iters = pass_index + 1;
+}
+
+// One block per problem: reduce + solve (the single-GPU iteration tail).
+__global__ void __launch_bounds__(256) k_solve(const ProbDesc *__restrict__ probs, ProbState *__restrict__ states,
+                                               const double *__restrict__ partials, SolveParams sp,
+                                               int pass_index) {
+    const ProbDesc pd = probs[blockIdx.x];
+    ProbState *st = states + blockIdx.x;
+    if (st->done) return;
+    __shared__ double sw[8][kAcc];
+    __shared__ double tot[kAcc];
+    reduce_partials(pd, partials, sw, tot);
+    if (threadIdx.x == 0) solve_from_totals(tot, (double)pd.npts, st, sp, pass_index);
+}
+
+// The same tail split in two for multi-GPU alignment of ONE cloud sharded over ranks (ICPRefinement's global
+// transform, src/evaluation.cpp:244-274): k_reduce leaves each problem's 32 totals in a device buffer the
+// caller all-reduces across GPUs, k_solve_totals finishes the iteration from the combined totals.  Every rank
+// sees identical totals, hence applies the identical update: no broadcast of T is needed.
+__global__ void __launch_bounds__(256) k_reduce(const ProbDesc *__restrict__ probs, const ProbState *__restrict__ states,
+                                                const double *__restrict__ partials, double *__restrict__ totals) {
+    const ProbDesc pd = probs[blockIdx.x];
+    __shared__ double sw[8][kAcc];
+    __shared__ double tot[kAcc];
+    if (states[blockIdx.x].done) {  // finished problems contribute their last totals unchanged
+        return;
+    }
+    reduce_partials(pd, partials, sw, tot);
+    if (threadIdx.x < kAcc) totals[(int64_t)blockIdx.x * kAcc + threadIdx.x] = tot[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(32) k_solve_totals(int P, ProbState *__restrict__ states,
+                                                     const double *__restrict__ totals,
+                                                     const double *__restrict__ npts_global, SolveParams sp,
+                                                     int pass_index) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P || states[p].done) return;
+    double tot[kAcc];
+    for (int i = 0; i < kAcc; i++) tot[i] = totals[(int64_t)p * kAcc + i];
+    solve_from_totals(tot, npts_global[p], states + p, sp, pass_index);
 }
 
 // ---- source-cloud bucket sort (spatial coherence for the search; deterministic order) ----------------
@@ -445,13 +484,17 @@ struct Batch {
     int *d_corr = nullptr;
     int64_t launches = 0;
     int iter_base = 0;                       // running pass index for vb200_batch_iterate
+    double *d_totals = nullptr;              // P x kAcc, library-owned unless the caller supplied a buffer
+    double *d_totals_ext = nullptr;
+    double *d_npts_global = nullptr;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // pass start / pass end = solve start / solve end
     bool ev_valid = false;
 };
 
 static void batch_free_problems(Batch *b) {
     cudaStream_t st = b->scene->stream;
-    void *ptrs[5] = {b->d_probs, b->d_states, b->d_tasks, b->d_partials, b->d_corr};
+    void *ptrs[7] = {b->d_probs, b->d_states, b->d_tasks, b->d_partials, b->d_corr, b->d_totals, b->d_npts_global};
+    b->d_totals = nullptr; b->d_npts_global = nullptr;
     for (void *q : ptrs)
         if (q) cudaFreeAsync(q, st);
     b->d_probs = nullptr; b->d_states = nullptr; b->d_tasks = nullptr; b->d_partials = nullptr; b->d_corr = nullptr;
@@ -603,6 +646,76 @@ static int batch_run(Batch *b, int estimator, const double *gravity, double max_
     return VB200_OK;
 }
 
+static int make_params(Batch *b, int estimator, const double *gravity, double max_dist, PassParams *pp,
+                       SolveParams *sp) {
+    Scene *sc = b->scene;
+    if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY) return VB200_ERR_INVALID;
+    if (!(max_dist > 0.0)) return VB200_ERR_DISTANCE;
+    if (max_dist > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
+    if (estimator != VB200_EST_P2P && (!b->has_normals || !sc->has_normals)) return VB200_ERR_NORMALS;
+    pp->r2 = (double)(float)(max_dist * max_dist);
+    pp->r2_ub = r2_upper_bound(sc->grid.p, pp->r2);
+    sp->estimator = estimator;
+    sp->g[0] = 0.0; sp->g[1] = 1.0; sp->g[2] = 0.0;
+    if (estimator == VB200_EST_P2PLANE_GRAVITY && gravity) {
+        double l = sqrt(gravity[0] * gravity[0] + gravity[1] * gravity[1] + gravity[2] * gravity[2]);
+        if (!(l > 0.0)) return VB200_ERR_INVALID;
+        for (int a = 0; a < 3; a++) sp->g[a] = gravity[a] / l;
+    }
+    return VB200_OK;
+}
+
+// first half of an iteration: correspondence pass + per-problem totals left on the device
+static int batch_pass(Batch *b, int estimator, double max_dist) {
+    Scene *sc = b->scene;
+    cudaStream_t st = sc->stream;
+    PassParams pp;
+    SolveParams sp;
+    VB_TRY(make_params(b, estimator, nullptr, max_dist, &pp, &sp));
+    if (b->P == 0) return VB200_OK;
+    if (!b->d_totals && !b->d_totals_ext) {
+        VB_CUDA(cudaMallocAsync((void **)&b->d_totals, sizeof(double) * kAcc * (size_t)b->P, st));
+        VB_CUDA(cudaMemsetAsync(b->d_totals, 0, sizeof(double) * kAcc * (size_t)b->P, st));
+    }
+    double *totals = b->d_totals_ext ? b->d_totals_ext : b->d_totals;
+    if (b->nblk) {
+        if (estimator != VB200_EST_P2P)
+            k_pass<1><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
+        else
+            k_pass<0><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
+        b->launches++;
+    }
+    k_reduce<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, totals);
+    b->launches++;
+    VB_CUDA(cudaGetLastError());
+    return VB200_OK;
+}
+
+// second half: finish the iteration from the (all-reduced) totals
+static int batch_solve(Batch *b, int estimator, const double *gravity, double max_dist, double rel_fitness,
+                       double rel_rmse, int max_iter, int pass_index, const int64_t *npts_global) {
+    Scene *sc = b->scene;
+    cudaStream_t st = sc->stream;
+    PassParams pp;
+    SolveParams sp;
+    VB_TRY(make_params(b, estimator, gravity, max_dist, &pp, &sp));
+    sp.rel_fitness = rel_fitness;
+    sp.rel_rmse = rel_rmse;
+    sp.max_iter = max_iter;
+    if (b->P == 0) return VB200_OK;
+    double *totals = b->d_totals_ext ? b->d_totals_ext : b->d_totals;
+    if (!totals) return VB200_ERR_INVALID;  // vb200_batch_pass has not run
+    if (!b->d_npts_global) VB_CUDA(cudaMallocAsync((void **)&b->d_npts_global, sizeof(double) * (size_t)b->P, st));
+    std::vector<double> np((size_t)b->P);
+    for (int p = 0; p < b->P; p++) np[p] = npts_global ? (double)npts_global[p] : (double)b->probs[p].npts;
+    VB_CUDA(cudaMemcpyAsync(b->d_npts_global, np.data(), sizeof(double) * (size_t)b->P, cudaMemcpyHostToDevice, st));
+    k_solve_totals<<<div_up(b->P, 32), 32, 0, st>>>(b->P, b->d_states, totals, b->d_npts_global, sp, pass_index);
+    b->launches++;
+    VB_CUDA(cudaGetLastError());
+    VB_CUDA(cudaStreamSynchronize(st));  // `np` is pageable host memory
+    return VB200_OK;
+}
+
 // n unconditional iterations from the current transforms (no convergence test, `done` never set)
 static int batch_iterate(Batch *b, int estimator, const double *gravity, double max_dist, int n_iter) {
     Scene *sc = b->scene;
@@ -657,6 +770,35 @@ extern "C" int vb200_batch_iterate(vb200_batch_t *batch, int estimator, const do
     Batch *b = reinterpret_cast<Batch *>(batch);
     VB_CUDA(cudaSetDevice(b->scene->device));
     return vb::batch_iterate(b, estimator, gravity_axis, max_dist, n_iter);
+}
+
+extern "C" int vb200_batch_pass(vb200_batch_t *batch, int estimator, double max_dist) {
+    if (!batch) return VB200_ERR_INVALID;
+    Batch *b = reinterpret_cast<Batch *>(batch);
+    VB_CUDA(cudaSetDevice(b->scene->device));
+    return vb::batch_pass(b, estimator, max_dist);
+}
+
+extern "C" int vb200_batch_set_totals_buffer(vb200_batch_t *batch, void *d_totals) {
+    if (!batch) return VB200_ERR_INVALID;
+    reinterpret_cast<Batch *>(batch)->d_totals_ext = (double *)d_totals;
+    return VB200_OK;
+}
+
+extern "C" void *vb200_batch_totals(vb200_batch_t *batch) {
+    if (!batch) return nullptr;
+    Batch *b = reinterpret_cast<Batch *>(batch);
+    return b->d_totals_ext ? b->d_totals_ext : b->d_totals;
+}
+
+extern "C" int vb200_batch_solve(vb200_batch_t *batch, int estimator, const double *gravity_axis, double max_dist,
+                                 double rel_fitness, double rel_rmse, int max_iter, int pass_index,
+                                 const int64_t *npts_global) {
+    if (!batch || pass_index < 0 || max_iter < 0) return VB200_ERR_INVALID;
+    Batch *b = reinterpret_cast<Batch *>(batch);
+    VB_CUDA(cudaSetDevice(b->scene->device));
+    return vb::batch_solve(b, estimator, gravity_axis, max_dist, rel_fitness, rel_rmse, max_iter, pass_index,
+                           npts_global);
 }
 
 extern "C" int vb200_batch_last_kernel_ms(vb200_batch_t *batch, float *pass_ms, float *solve_ms) {

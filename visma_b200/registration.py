@@ -217,6 +217,21 @@ class Batch:
         check(lib().vb200_batch_iterate(self._h, estimation.kind, _dp(g), float(max_dist), int(n_iter)),
               "vb200_batch_iterate")
 
+    # --- iteration split at the cross-GPU exchange point (see include/visma_b200.h) ---
+    def set_totals_buffer(self, device_ptr):
+        check(lib().vb200_batch_set_totals_buffer(self._h, C.c_void_p(device_ptr)), "vb200_batch_set_totals_buffer")
+
+    def pass_(self, estimation, max_dist):
+        check(lib().vb200_batch_pass(self._h, estimation.kind, float(max_dist)), "vb200_batch_pass")
+
+    def solve(self, estimation, max_dist, criteria, pass_index, npts_global=None):
+        g = getattr(estimation, "gravity_axis", None)
+        g = _f64(g) if g is not None else None
+        n = None if npts_global is None else np.ascontiguousarray(npts_global, np.int64)
+        check(lib().vb200_batch_solve(self._h, estimation.kind, _dp(g), float(max_dist), criteria.relative_fitness_,
+                                      criteria.relative_rmse_, criteria.max_iteration_, int(pass_index),
+                                      None if n is None else _i64p(n)), "vb200_batch_solve")
+
     def last_kernel_ms(self):
         a, b = C.c_float(), C.c_float()
         check(lib().vb200_batch_last_kernel_ms(self._h, C.byref(a), C.byref(b)), "vb200_batch_last_kernel_ms")

@@ -107,23 +107,17 @@ class Renderer:
             if n else np.zeros((0, 16), np.float32)
         return n, V, v_off, F, f_off, M
 
-    def RenderDepthBatch(self, models, meshes=None, want_z24=False):
+    def RenderDepthBatch(self, models, meshes=None, want_z24=False, out_depth=None, out_z24=None):
         """Batch form: one depth map per model pose.  meshes = optional list of (V, F), one per pose;
-        default = the mesh set with SetMesh for every pose."""
-        n = len(models)
-        if meshes is None:
-            meshes = [(self.V_, self.F_)] * n
-        Vs = [np.ascontiguousarray(np.asarray(v, np.float32).reshape(-1, 3)) for v, _ in meshes]
-        Fs = [np.ascontiguousarray(np.asarray(f, np.int32).reshape(-1, 3)) for _, f in meshes]
-        v_off = np.zeros(n + 1, np.int64); v_off[1:] = np.cumsum([len(v) for v in Vs])
-        f_off = np.zeros(n + 1, np.int64); f_off[1:] = np.cumsum([len(f) for f in Fs])
-        V = np.ascontiguousarray(np.concatenate(Vs)) if n else np.zeros((0, 3), np.float32)
-        F = np.ascontiguousarray(np.concatenate(Fs)) if n else np.zeros((0, 3), np.int32)
-        M = np.ascontiguousarray(np.stack([np.asarray(m, np.float32).reshape(4, 4).T.reshape(-1) for m in models])) \
-            if n else np.zeros((0, 16), np.float32)
+        default = the mesh set with SetMesh for every pose.  out_depth / out_z24: optional caller-owned
+        n x H x W float32 / uint32 arrays (e.g. pinned) reused across calls."""
+        n, V, v_off, F, f_off, M = self._pack(models, meshes)
         H, W = self.rows_, self.cols_
-        depth = np.empty((n, H, W), np.float32)
-        z24 = np.empty((n, H, W), np.uint32) if want_z24 else None
+        depth = out_depth if out_depth is not None else np.empty((n, H, W), np.float32)
+        z24 = out_z24 if out_z24 is not None else (np.empty((n, H, W), np.uint32) if want_z24 else None)
+        for a, t in ((depth, np.float32), (z24, np.uint32)):
+            if a is not None and (a.shape != (n, H, W) or a.dtype != t or not a.flags.c_contiguous):
+                raise ValueError("output buffers must be C-contiguous %d x %d x %d %s" % (n, H, W, t.__name__))
         fp = C.POINTER(C.c_float)
         check(lib().vb200_render_depth_batch(
             V.ctypes.data_as(fp), v_off.ctypes.data_as(C.POINTER(C.c_int64)),
@@ -132,7 +126,7 @@ class Renderer:
             self.cx_, self.cy_, H, W, self.device,
             None if z24 is None else z24.ctypes.data_as(C.POINTER(C.c_uint32)), depth.ctypes.data_as(fp)),
             "vb200_render_depth_batch")
-        return (depth, z24) if want_z24 else depth
+        return (depth, z24) if z24 is not None else depth
 
     # accessors (render/renderer.h:96-109)
     def fx(self): return self.fx_

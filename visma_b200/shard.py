@@ -68,3 +68,35 @@ def register_sharded(scene, sources, inits, max_dist, estimation, criteria=None,
                                    np.asarray([inits[b] for b in mine]).reshape(-1, 4, 4), estimation, criteria,
                                    want_corr=False) if mine else []
     return all_gather_poses(pack_results(res, len(sources), rank, world), len(sources), device, group)
+
+
+def register_global_sharded(scene, source_shard, init, max_dist, estimation, criteria=None, device=None,
+                            group=None):
+    """ONE ICP problem whose source cloud is sharded over the ranks (ICPRefinement's global transform,
+    src/evaluation.cpp:244-274): every rank searches its shard against its scene replica, the 32 per-problem
+    totals are all-reduced (the path's one per-iteration collective: 256 bytes), and every rank applies the
+    identical estimator update.  Returns the RegistrationResult (same on every rank)."""
+    import torch
+    import torch.distributed as dist
+    from . import registration as reg
+    criteria = criteria or reg.ICPConvergenceCriteria()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = device if device is not None else torch.device("cuda", scene.device)
+    batch = reg.Batch(scene, [source_shard])
+    batch.set_problems(np.asarray(init, np.float64).reshape(1, 16))
+    totals = torch.zeros(32, dtype=torch.float64, device=dev)
+    batch.set_totals_buffer(totals.data_ptr())
+    n_local = torch.tensor([batch.sizes[0]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(n_local, group=group)
+    n_global = [int(n_local.item())]
+    for it in range(criteria.max_iteration_ + 1):
+        batch.pass_(estimation, max_dist)
+        scene.sync()                      # totals written on the library's stream
+        if world > 1:
+            dist.all_reduce(totals, group=group)
+            torch.cuda.synchronize(dev)
+        batch.solve(estimation, max_dist, criteria, it, n_global)
+    res = batch.results()[0]
+    batch.close()
+    return res
