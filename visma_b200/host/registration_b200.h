@@ -178,6 +178,19 @@ inline std::shared_ptr<open3d::PointCloud> VoxelDownSample(const open3d::PointCl
     return output;
 }
 
+/// feh::SamplePointCloudFromMesh (include/geometry.h:29-64) on the GPU; V: n x 3 float row-major, F: m x 3 int.
+/// Reproducible from `seed` (the reference seeds from the wall clock).
+inline std::vector<Eigen::Vector3d> SamplePointCloudFromMesh(const float *V, int64_t nV, const int *F, int64_t nF,
+                                                             int max_num_pts = 1000, uint64_t seed = 0,
+                                                             int device = 0) {
+    std::vector<Eigen::Vector3d> out((size_t)std::max(max_num_pts, 0));
+    if (out.empty()) return out;
+    int rc = vb200_sample_mesh(V, nV, F, nF, max_num_pts, seed, device, reinterpret_cast<double *>(out.data()),
+                               nullptr);
+    if (rc != VB200_OK) out.clear();
+    return out;
+}
+
 }  // namespace visma_b200
 
 #ifdef VISMA_B200_WITH_CICP

@@ -78,6 +78,11 @@ public:
                                      vb200_last_error());
     }
 
+    /// RenderEdge / RenderMask (render/renderer.h:82-97): out = rows x cols bytes.  The edge pass linearises
+    /// depth with the shader's own fixed uniforms z_near = 0.05, z_far = 2.0 (render/renderer.cpp:95-96).
+    void RenderEdge(const Mat4fc &model, uint8_t *out) { EdgeMask(model, out, nullptr); }
+    void RenderMask(const Mat4fc &model, uint8_t *out) { EdgeMask(model, nullptr, out); }
+
     float fx() const { return fx_; }
     float fy() const { return fy_; }
     float cx() const { return cx_; }
@@ -90,6 +95,16 @@ public:
     int rows() const { return rows_; }
 
 private:
+    void EdgeMask(const Mat4fc &model, uint8_t *edge, uint8_t *mask) {
+        int64_t voff[2] = {0, (int64_t)(V_.size() / 3)}, foff[2] = {0, (int64_t)(F_.size() / 3)};
+        int rc = vb200_render_edge_mask_batch(V_.data(), voff, F_.data(), foff, 1, model.data(), pose_.data(), z_near_,
+                                              z_far_, fx_, fy_, cx_, cy_, rows_, cols_, device_, 0.05f, 2.0f, edge,
+                                              mask, 0);
+        if (rc != VB200_OK)
+            throw std::runtime_error(std::string("visma_b200::Renderer: ") + vb200_strerror(rc) + " " +
+                                     vb200_last_error());
+    }
+
     int rows_, cols_, device_;
     float fx_ = 0, fy_ = 0, cx_ = 0, cy_ = 0, z_near_ = 0.05f, z_far_ = 10.0f;
     Mat4fc pose_;
