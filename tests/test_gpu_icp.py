@@ -261,7 +261,6 @@ def test_split_iteration_equals_fused(vb, scene, name):
     ra, rb = batches[0].results()[0], batches[1].results()[0]
     assert np.array_equal(ra.transformation_, rb.transformation_)  # ranks stay consistent without a broadcast
     assert ra.fitness_ == rb.fitness_ and ra.iterations_ == rb.iterations_
-    rot, tr = vb.synth.pose_error(ra.transformation_, whole.transformation_)
-    assert rot < 1e-9 and tr < 1e-9
+    assert np.allclose(ra.transformation_, whole.transformation_, atol=1e-9, rtol=0)
     assert abs(ra.fitness_ - whole.fitness_) <= 1.0 / len(src) and abs(ra.inlier_rmse_ - whole.inlier_rmse_) < 1e-9
     assert ra.iterations_ == whole.iterations_

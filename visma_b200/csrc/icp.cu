@@ -516,6 +516,7 @@ static void batch_free(Batch *b) {
 static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int ncloud) {
     Scene *sc = b->scene;
     cudaStream_t st = sc->stream;
+    if (ncloud > 32768) return VB200_ERR_INVALID;  // bucket table = ncloud x 32768 counters (int indexed)
     b->ncloud = ncloud;
     b->cloud_off.resize((size_t)ncloud + 1);
     for (int c = 0; c <= ncloud; c++) {

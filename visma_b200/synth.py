@@ -149,5 +149,7 @@ def pose_error(T, T_ref):
     """(rotation angle in rad, translation distance in m) between two rigid transforms —
     MeasurePoseError semantics (include/geometry.h:147-180)."""
     dR = T[:3, :3] @ T_ref[:3, :3].T
-    c = np.clip((np.trace(dR) - 1.0) / 2.0, -1.0, 1.0)
-    return float(np.arccos(c)), float(np.linalg.norm(T[:3, 3] - T_ref[:3, 3]))
+    # atan2 of the skew part and the trace: accurate near zero (arccos alone bottoms out at ~1e-8)
+    w = 0.5 * np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]])
+    ang = np.arctan2(np.linalg.norm(w), (np.trace(dR) - 1.0) / 2.0)
+    return float(ang), float(np.linalg.norm(T[:3, 3] - T_ref[:3, 3]))
