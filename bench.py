@@ -33,6 +33,15 @@ METRIC = "icp_iterations_per_s_2Mpt_scene_x32_objects"
 UNIT = "iterations/s"
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def env_int(k, d):
     return int(os.environ.get(k, d))
 
@@ -83,6 +92,12 @@ class ClockSampler:
         for line in self.p.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_ready(self, timeout=3.0):
+        """nvidia-smi takes a few hundred ms to start: do not enter the timed region before it samples."""
+        t0 = time.perf_counter()
+        while self.p and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self):
         if self.p:
             self.p.terminate()
@@ -126,7 +141,7 @@ def run_reference(args):
         return  # the CPU baseline runs once, on rank 0's host cores
     from oracle import pyref
     if not pyref.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvisma_ref.so not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libvisma_ref.so not built"})
         return
     pyref.set_num_threads(os.cpu_count() or 1)
     cores = pyref.num_threads()
@@ -150,7 +165,7 @@ def run_reference(args):
                              "sample": "%d of 32 objects per step, x%d steps, scaled to 32" % (n_s, args.steps)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -190,14 +205,16 @@ def run_ours(args):
         return p_ms, s_ms
 
     # ---- device-resident leg ("value")
+    sampler = ClockSampler(local)
+    sampler.start()
     batch.set_problems(d["T_init"])
     for _ in range(args.warmup):
         one_step(False)
     batch.set_problems(d["T_init"])      # timed steps replay the real trajectory from the initial poses
     launches0 = batch.launches()
-    sampler = ClockSampler(local)
+    sampler.wait_ready()
+    sampler.rows.clear()                 # keep only samples taken from here on (timed legs)
     barrier()
-    sampler.start()
     pass_ms, solve_ms = [], []
     for _ in range(args.steps):
         p_ms, s_ms = one_step(True)
@@ -326,9 +343,19 @@ def run_ours(args):
                          "algorithmic_bytes": b_alg},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    communicator creation), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved
+    original descriptor."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -339,6 +366,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global _REAL_STDOUT
+    _REAL_STDOUT = claim_stdout()
     if args.impl == "reference":
         if args.steps == 30 and "--steps" not in " ".join(sys.argv):
             args.steps = 2
