@@ -1,6 +1,8 @@
 """Host math of the annotation driver mirror (src/annotation.cpp:78-96, include/geometry.h:18-26,
 core/utils.h:229-233) — CPU only — and, on the GPU, the whole orientation-constrained flow and the
 ICPRefinement flow against the same flows driven by the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -79,3 +81,42 @@ def test_icp_refinement_flow(vb, oracle):
     opts["use_point_to_plane"] = True
     res, _ = an.ICPRefinement(d["scene_xyz"], clouds, list(d["T_gt"]), off, opts)
     assert np.array_equal(res.transformation_, off) and res.fitness_ == 0
+
+
+def test_savemat_format(tmp_path):
+    """feh::SaveMat layout (core/utils.h:359-373), read back the way misc/show_2Dmap.py:16-21 does."""
+    from visma_b200 import io2d
+    rng = np.random.default_rng(1)
+    for arr in (rng.random((7, 5)).astype(np.float32), rng.integers(0, 255, (4, 9)).astype(np.uint8)):
+        f = tmp_path / "m.bin"
+        io2d.SaveMat(str(f), arr)
+        raw = open(f, "rb").read()
+        h, w = np.frombuffer(raw[:8], np.int32)
+        assert (h, w) == arr.shape and len(raw) == 8 + arr.nbytes
+        assert (np.frombuffer(raw[8:], arr.dtype).reshape(h, w) == arr).all()
+        assert (io2d.LoadMat(str(f), arr.dtype) == arr).all()
+
+
+@pytest.mark.gpu
+def test_render_depth_tool(vb, oracle, tmp_path):
+    """scripts/render_depth.py on the reference's own config values (misc/render_depth.json)."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from visma_b200 import io2d
+    cfg = {"major_version": 3, "minor_version": 3, "fx": 400, "fy": 400, "z_far": 10, "mesh": "misc/hermanmiller_aeron.obj",
+           "translation": [0, 0, 1], "show": False, "save": True, "output_path": str(tmp_path), "mask": True}
+    p = tmp_path / "render_depth.json"
+    p.write_text("// comments are legal in the reference's configs\n" + json.dumps(cfg))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "render_depth.py"), str(p)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    depth = io2d.LoadMat(str(tmp_path / "depthmap.bin"), np.float32)
+    mask = io2d.LoadMat(str(tmp_path / "mask.bin"), np.uint8)
+    V, F = vb.synth.load_chair()
+    P = oracle.projection(0.05, 10.0, 400.0, 400.0, 320.0, 400.0, 480, 640)   # cy := fy, render_depth.cpp:31
+    oz, od = oracle.render_depth(V, F, vb.synth.make_T(np.eye(3), [0, 0, 1.0]).astype(np.float32).T.reshape(-1),
+                                 oracle.view(np.eye(4, dtype=np.float32).reshape(-1)), P, 480, 640)
+    assert depth.shape == (480, 640) and (depth == od).all()
+    assert (mask == oracle.render_mask(oz)).all()

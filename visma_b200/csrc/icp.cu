@@ -377,12 +377,13 @@ __global__ void __launch_bounds__(256) k_src_scatter(const double *__restrict__ 
     sidx[start[kk] + atomicAdd(cursor + kk, 1)] = ((sz * 4 + sy * 2 + sx) << kSubShift) | i;
 }
 
-__global__ void __launch_bounds__(128) k_src_sort_buckets(int nbuckets, const int *__restrict__ start,
+// one WARP per bucket (most of the ncloud x 32768 buckets are empty and exit at once)
+__global__ void __launch_bounds__(256) k_src_sort_buckets(int nbuckets, const int *__restrict__ start,
                                                           int *__restrict__ sidx) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (b >= nbuckets) return;
-    int s0 = start[b], s1 = start[b + 1];
-    if (s1 - s0 > 1) cell_sort(sidx + s0, s1 - s0);
+    const int s0 = start[b], s1 = start[b + 1];
+    if (s1 - s0 > 1) warp_cell_sort<int, 8>(sidx + s0, s1 - s0);
 }
 
 __global__ void __launch_bounds__(256) k_src_gather(const double *__restrict__ in, int n,
@@ -548,7 +549,7 @@ static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int
     VB_TRY(exclusive_scan_i32(d_counts.p, d_start.p, (int64_t)nb, nullptr, st));
     VB_CUDA(cudaMemsetAsync(d_counts.p, 0, sizeof(int) * nb, st));
     k_src_scatter<<<div_up(n, 256), 256, 0, st>>>(d_in.p, d_key.p, n, 4.0 / sc->grid.p.cell, d_start.p, d_counts.p, d_sidx.p);
-    k_src_sort_buckets<<<div_up((int64_t)nb - 1, 128), 128, 0, st>>>((int)nb - 1, d_start.p, d_sidx.p);
+    k_src_sort_buckets<<<div_up(((int64_t)nb - 1) * 32, 256), 256, 0, st>>>((int)nb - 1, d_start.p, d_sidx.p);
     k_src_gather<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, d_sidx.p, b->d_cloud_off, ncloud, b->d_src, b->d_src_orig);
     VB_CUDA(cudaGetLastError());
     b->launches += 4 + 3;

@@ -55,20 +55,30 @@ __global__ void __launch_bounds__(kTpb) k_scatter(const int *__restrict__ ckey,
     skey[pos] = ((unsigned long long)fbit[i] << 32) | (unsigned long long)(unsigned int)i;
 }
 
-__global__ void __launch_bounds__(128) k_sort_cells(int ncoarse, const int *__restrict__ cstart,
+// one WARP per coarse cell: order its keys by (fine cell, index), OR the fine-cell bits into the occupancy mask
+__global__ void __launch_bounds__(256) k_sort_cells(int ncoarse, const int *__restrict__ cstart,
                                                     unsigned long long *__restrict__ skey,
                                                     unsigned long long *__restrict__ cmask,
                                                     int *__restrict__ cfcount) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncoarse) return;
-    int s0 = cstart[c], s1 = cstart[c + 1];
-    unsigned long long m = 0ull;
+    const int c = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= ncoarse) return;  // warp-uniform
+    const int s0 = cstart[c], s1 = cstart[c + 1];
+    unsigned lo = 0u, hi = 0u;
     if (s1 > s0) {
-        cell_sort(skey + s0, s1 - s0);
-        for (int s = s0; s < s1; s++) m |= 1ull << (unsigned)(skey[s] >> 32);
+        warp_cell_sort<unsigned long long, 16>(skey + s0, s1 - s0);
+        for (int s = s0 + lane; s < s1; s += 32) {
+            const unsigned b = (unsigned)(skey[s] >> 32);
+            if (b < 32u) lo |= 1u << b; else hi |= 1u << (b - 32u);
+        }
     }
-    cmask[c] = m;
-    cfcount[c] = __popcll(m);
+    lo = __reduce_or_sync(0xffffffffu, lo);
+    hi = __reduce_or_sync(0xffffffffu, hi);
+    if (lane == 0) {
+        const unsigned long long m = ((unsigned long long)hi << 32) | lo;
+        cmask[c] = m;
+        cfcount[c] = __popcll(m);
+    }
 }
 
 __global__ void __launch_bounds__(128) k_fine_starts(int ncoarse, const int *__restrict__ cstart,
@@ -192,8 +202,8 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     VB_CUDA(cudaMemsetAsync(d_ccount.p, 0, sizeof(int) * ((size_t)ncoarse + 1), st));  // reuse as cursors
     k_scatter<<<div_up(n, kTpb), kTpb, 0, st>>>(d_ckey.p, d_fbit.p, n, d_cstart.p, d_ccount.p, d_skey.p);
     VB_CUDA(cudaGetLastError());
-    k_sort_cells<<<div_up(ncoarse, 128), 128, 0, st>>>((int)ncoarse, d_cstart.p, d_skey.p, d_cmask.p,
-                                                        d_cfcount.p);
+    k_sort_cells<<<div_up(ncoarse * 32, 256), 256, 0, st>>>((int)ncoarse, d_cstart.p, d_skey.p, d_cmask.p,
+                                                             d_cfcount.p);
     VB_CUDA(cudaGetLastError());
     VB_TRY(exclusive_scan_i32(d_cfcount.p, d_cbase.p, ncoarse + 1, d_total.p, st));
     int nfine = 0;
@@ -266,7 +276,7 @@ int grid_order_points(const Scene *sc, const double *d_xyz, int64_t n, int *d_pe
     VB_TRY(exclusive_scan_i32(d_ccount.p, d_cstart.p, ncoarse + 1, nullptr, st));
     VB_CUDA(cudaMemsetAsync(d_ccount.p, 0, sizeof(int) * ((size_t)ncoarse + 1), st));
     k_scatter<<<div_up(n, kTpb), kTpb, 0, st>>>(d_ckey.p, d_fbit.p, n, d_cstart.p, d_ccount.p, d_skey.p);
-    k_sort_cells<<<div_up(ncoarse, 128), 128, 0, st>>>((int)ncoarse, d_cstart.p, d_skey.p, d_cmask.p, d_cfcount.p);
+    k_sort_cells<<<div_up(ncoarse * 32, 256), 256, 0, st>>>((int)ncoarse, d_cstart.p, d_skey.p, d_cmask.p, d_cfcount.p);
     k_perm_from_keys<<<div_up(n, 256), 256, 0, st>>>(d_skey.p, n, d_perm);
     VB_CUDA(cudaGetLastError());
     return VB200_OK;
