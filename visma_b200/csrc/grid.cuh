@@ -350,6 +350,56 @@ __device__ __forceinline__ void scan_box_uniform(const GridDev &G, const QueryCt
             }
 }
 
+// Phase-2 scan in rounds.  Each active lane asks for the cells within `want` (squared metric reach) that lie
+// beyond what it has already completed (`done`); a cell is scanned when some active lane asks for it and no
+// member has it inside its completed region (then it was scanned in an earlier round).  Lanes that still have
+// no candidate grow their reach one fine cell per round instead of jumping to the full radius — an empty home
+// cell next to a populated surface would otherwise drag the whole warp through every cell of the radius ball.
+// thr_end returns the lane's final threshold: every cell with gap2 <= thr_end has been scanned.
+__device__ __forceinline__ void scan_box_annulus(const GridDev &G, const QueryCtx &c, const LanePos &lp, bool member,
+                                                 bool active, const FineBox &box, const FineBox &skip, float want,
+                                                 float done, float r2_ub, Screen &r, float &thr_end) {
+    const GridParams &g = G.p;
+    const float fine2 = g.fine * g.fine * 0.998f;  // deflated: never prune a cell that could matter
+    float thr = want;
+    for (int cz = box.z0 >> 2; cz <= (box.z1 >> 2); ++cz)
+        for (int cy = box.y0 >> 2; cy <= (box.y1 >> 2); ++cy)
+            for (int cx = box.x0 >> 2; cx <= (box.x1 >> 2); ++cx) {
+                const CoarseCell cc = G.coarse[((int64_t)cz * g.cdim[1] + cy) * g.cdim[0] + cx];
+                const unsigned long long m = cc.mask;
+                if (m == 0ull) continue;
+                unsigned long long sel = m & range_mask(max(box.x0 - 4 * cx, 0), min(box.x1 - 4 * cx, 3),
+                                                        max(box.y0 - 4 * cy, 0), min(box.y1 - 4 * cy, 3),
+                                                        max(box.z0 - 4 * cz, 0), min(box.z1 - 4 * cz, 3));
+                {
+                    int ax = max(skip.x0 - 4 * cx, 0), bx = min(skip.x1 - 4 * cx, 3);
+                    int ay = max(skip.y0 - 4 * cy, 0), by = min(skip.y1 - 4 * cy, 3);
+                    int az = max(skip.z0 - 4 * cz, 0), bz = min(skip.z1 - 4 * cz, 3);
+                    if (ax <= bx && ay <= by && az <= bz) sel &= ~range_mask(ax, bx, ay, by, az, bz);
+                }
+                if (sel == 0ull) continue;
+                const float rx = lp.ux - (float)(4 * cx), ry = lp.uy - (float)(4 * cy), rz = lp.uz - (float)(4 * cz);
+                while (sel) {
+                    const int b = __ffsll((long long)sel) - 1;
+                    sel &= sel - 1ull;
+                    const float fx = small_int_to_float(b & 3), fy = small_int_to_float((b >> 2) & 3),
+                                fz = small_int_to_float(b >> 4);
+                    const float ex = fmaxf(fmaxf(fx - rx, rx - fx - 1.0f), 0.0f);
+                    const float ey = fmaxf(fmaxf(fy - ry, ry - fy - 1.0f), 0.0f);
+                    const float ez = fmaxf(fmaxf(fz - rz, rz - fz - 1.0f), 0.0f);
+                    const float gap2 = (ex * ex + ey * ey + ez * ez) * fine2;
+                    const bool asks = active && gap2 <= thr && gap2 > done;
+                    const bool had = member && gap2 <= done;
+                    if (!__any_sync(0xffffffffu, asks) || __any_sync(0xffffffffu, had)) continue;
+                    const int rank = __popcll(m & ((1ull << b) - 1ull));
+                    const int s0 = __ldg(G.fstart + cc.base + rank), s1 = __ldg(G.fstart + cc.base + rank + 1);
+                    scan_run(G.hi, s0, s1, c, r);
+                    if (r.bs >= 0) thr = fminf(thr, reach_of(g, r.best, r2_ub));
+                }
+            }
+    thr_end = thr;
+}
+
 #ifndef VB_GROUP_HW
 #define VB_GROUP_HW 2
 #endif
@@ -384,20 +434,34 @@ __device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, cons
         b0.y0 = __reduce_min_sync(FULL, member ? c.gy : 0x7fffffff); b0.y1 = __reduce_max_sync(FULL, member ? c.gy : -0x7fffffff);
         b0.z0 = __reduce_min_sync(FULL, member ? c.gz : 0x7fffffff); b0.z1 = __reduce_max_sync(FULL, member ? c.gz : -0x7fffffff);
         scan_box_uniform<false, false>(G, cq, lp, member, b0, b0, r2_ub, rr);
-        // phase 2: grow the box to cover every member's reach, skipping what phase 1 already scanned
-        const float rho = sqrtf(reach_of(g, rr.best, r2_ub)) / g.fine * 1.001f + 1e-4f;
-        // per-lane need: the fine cells its reach touches
-        FineBox need;
-        need.x0 = c.gx - (int)ceilf(fmaxf(rho - c.fx, 0.0f)); need.x1 = c.gx + (int)ceilf(fmaxf(rho - (1.0f - c.fx), 0.0f));
-        need.y0 = c.gy - (int)ceilf(fmaxf(rho - c.fy, 0.0f)); need.y1 = c.gy + (int)ceilf(fmaxf(rho - (1.0f - c.fy), 0.0f));
-        need.z0 = c.gz - (int)ceilf(fmaxf(rho - c.fz, 0.0f)); need.z1 = c.gz + (int)ceilf(fmaxf(rho - (1.0f - c.fz), 0.0f));
-        FineBox b1;
-        b1.x0 = __reduce_min_sync(FULL, member ? need.x0 : 0x7fffffff); b1.x1 = __reduce_max_sync(FULL, member ? need.x1 : -0x7fffffff);
-        b1.y0 = __reduce_min_sync(FULL, member ? need.y0 : 0x7fffffff); b1.y1 = __reduce_max_sync(FULL, member ? need.y1 : -0x7fffffff);
-        b1.z0 = __reduce_min_sync(FULL, member ? need.z0 : 0x7fffffff); b1.z1 = __reduce_max_sync(FULL, member ? need.z1 : -0x7fffffff);
-        b1.x0 = max(b1.x0, 0); b1.y0 = max(b1.y0, 0); b1.z0 = max(b1.z0, 0);
-        b1.x1 = min(b1.x1, g.fdim[0] - 1); b1.y1 = min(b1.y1, g.fdim[1] - 1); b1.z1 = min(b1.z1, g.fdim[2] - 1);
-        if (!box_empty(b1)) scan_box_uniform<true, true>(G, cq, lp, member, b1, b0, r2_ub, rr);
+        // phase 2, in rounds: members with a candidate ask for their exact reach (one round); members without
+        // one grow their reach a fine cell per round until something turns up or the radius is exhausted
+        bool fin = !member;
+        float done = -1.0f;
+        for (int round = 1;; ++round) {
+            const bool active = member && !fin;
+            if (!__any_sync(FULL, active)) break;
+            const float ringr = (float)round * g.fine;
+            const float want = rr.bs >= 0 ? reach_of(g, rr.best, r2_ub) : fminf(ringr * ringr, r2_ub);
+            const float rho = sqrtf(want) / g.fine * 1.001f + 1e-4f;
+            FineBox need;
+            need.x0 = c.gx - (int)ceilf(fmaxf(rho - c.fx, 0.0f)); need.x1 = c.gx + (int)ceilf(fmaxf(rho - (1.0f - c.fx), 0.0f));
+            need.y0 = c.gy - (int)ceilf(fmaxf(rho - c.fy, 0.0f)); need.y1 = c.gy + (int)ceilf(fmaxf(rho - (1.0f - c.fy), 0.0f));
+            need.z0 = c.gz - (int)ceilf(fmaxf(rho - c.fz, 0.0f)); need.z1 = c.gz + (int)ceilf(fmaxf(rho - (1.0f - c.fz), 0.0f));
+            FineBox b1;
+            b1.x0 = __reduce_min_sync(FULL, active ? need.x0 : 0x7fffffff); b1.x1 = __reduce_max_sync(FULL, active ? need.x1 : -0x7fffffff);
+            b1.y0 = __reduce_min_sync(FULL, active ? need.y0 : 0x7fffffff); b1.y1 = __reduce_max_sync(FULL, active ? need.y1 : -0x7fffffff);
+            b1.z0 = __reduce_min_sync(FULL, active ? need.z0 : 0x7fffffff); b1.z1 = __reduce_max_sync(FULL, active ? need.z1 : -0x7fffffff);
+            b1.x0 = max(b1.x0, 0); b1.y0 = max(b1.y0, 0); b1.z0 = max(b1.z0, 0);
+            b1.x1 = min(b1.x1, g.fdim[0] - 1); b1.y1 = min(b1.y1, g.fdim[1] - 1); b1.z1 = min(b1.z1, g.fdim[2] - 1);
+            float thr_end = want;
+            if (!box_empty(b1)) scan_box_annulus(G, cq, lp, member, active, b1, b0, want, done, r2_ub, rr, thr_end);
+            if (active) {
+                // complete once the need computed from the final best fits inside what this round covered
+                fin = want >= r2_ub || (rr.bs >= 0 && reach_of(g, rr.best, r2_ub) <= want);
+                done = thr_end;
+            }
+        }
         if (member) r = rr;
     }
     if (!valid || r.bs < 0) return -1;
