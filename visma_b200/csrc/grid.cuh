@@ -405,18 +405,16 @@ __device__ __forceinline__ void scan_box_annulus(const GridDev &G, const QueryCt
 #endif
 constexpr int kGroupHalfWidth = VB_GROUP_HW;  // lanes within +-2 fine cells of the leader are searched together
 
-// All 32 lanes of the warp must call this together.  `valid` = this lane has a query inside the grid.
-__device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, const QueryCtx &c, double qx, double qy,
-                                              double qz, double r2, float r2_ub, double *d2_out) {
+// f32 screening for the lanes of `pending` (warp-uniform mask), searched group by group.  All 32 lanes of
+// the warp must call this together; lanes outside `pending` ride along and get an empty Screen back.
+__device__ __forceinline__ Screen coop_screen(const GridDev &G, unsigned pending, const QueryCtx &c, float r2_ub) {
     const unsigned FULL = 0xffffffffu;
     const GridParams &g = G.p;
-    *d2_out = 0.0;
     Screen r;
     r.best = r2_ub; r.second = 3.0e38f; r.bs = -1;
     LanePos lp;
     lp.ux = (float)c.gx + c.fx; lp.uy = (float)c.gy + c.fy; lp.uz = (float)c.gz + c.fz;
     const int lane = threadIdx.x & 31;
-    unsigned pending = __ballot_sync(FULL, valid);
     while (pending) {
         const int leader = __ffs(pending) - 1;
         const int lgx = __shfl_sync(FULL, c.gx, leader), lgy = __shfl_sync(FULL, c.gy, leader),
@@ -464,8 +462,16 @@ __device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, cons
         }
         if (member) r = rr;
     }
-    if (!valid || r.bs < 0) return -1;
-    // decide in double (per lane)
+    return r;
+}
+
+// The decision in double from a completed f32 screening (per lane): the winner's exact d2 against the
+// reference's threshold, or the double re-walk when the f32 result is ambiguous.
+__device__ __forceinline__ int nn_decide(const GridDev &G, const Screen &r, const QueryCtx &c, double qx, double qy,
+                                         double qz, double r2, float r2_ub, double *d2_out) {
+    const GridParams &g = G.p;
+    *d2_out = 0.0;
+    if (r.bs < 0) return -1;
     const float bb = band(g, r.best);
     if (r.second - r.best > bb + band(g, r.second)) {
         const double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)r.bs);
@@ -473,6 +479,234 @@ __device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, cons
         return -1;
     }
     return nn_exact_rescan(G, c, qx, qy, qz, r2, fminf(r.best + 2.0f * bb, r2_ub), d2_out);
+}
+
+// All 32 lanes of the warp must call this together.  `valid` = this lane has a query inside the grid.
+__device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, const QueryCtx &c, double qx, double qy,
+                                              double qz, double r2, float r2_ub, double *d2_out) {
+    const Screen r = coop_screen(G, __ballot_sync(0xffffffffu, valid), c, r2_ub);
+    *d2_out = 0.0;
+    if (!valid) return -1;
+    return nn_decide(G, r, c, qx, qy, qz, r2, r2_ub, d2_out);
+}
+
+// ---- lane-private search ----------------------------------------------------------------------------------
+// The cooperative walk above makes every lane of a group evaluate every candidate ANY member needs: ~100-170
+// candidates per 32 queries where each query alone needs 10-30.  Once a lane has a bound on its answer — the
+// distance to its match of the previous ICP iteration (`prior`), or the best candidate of its own home cell —
+// its reach is a fraction of a fine cell and the cells it needs are few.  Such a lane lists ITS cells (runs of
+// the sorted arrays) in a private column of shared memory and scans only those in a flat loop: neighbouring
+// lanes walk the same runs in step, so the loads still coalesce to a handful of 16-byte segments, but the
+// warp's trip count is the LARGEST lane's candidate count instead of the union's.  Lanes without a bound, with
+// a reach beyond kLaneMaxRho fine cells, or with more than kLaneMaxRuns cells fall back to coop_screen.  The
+// screening rule (every candidate within best + 2*band scanned, ambiguity flagged) is the same, so results are
+// those of the other searches, bit for bit.
+#ifndef VB_LANE_MAX_RUNS
+#define VB_LANE_MAX_RUNS 16
+#endif
+#ifndef VB_LANE_MAX_RHO_PCT
+#define VB_LANE_MAX_RHO_PCT 125
+#endif
+constexpr int kLaneMaxRuns = VB_LANE_MAX_RUNS;
+constexpr float kLaneMaxRho = VB_LANE_MAX_RHO_PCT * 0.01f;  // largest reach (fine-cell units) searched per lane
+#ifndef VB_LANE_PROBE_RHO_PCT
+#define VB_LANE_PROBE_RHO_PCT 50
+#endif
+constexpr float kLaneProbeRho = VB_LANE_PROBE_RHO_PCT * 0.01f;  // first reach of a lane that has no bound yet
+constexpr unsigned kRunLenBits = 12, kRunLenMask = (1u << kRunLenBits) - 1u;
+
+#ifdef VB_STATS
+__device__ unsigned long long g_stats[16];
+#define VB_STAT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
+#else
+#define VB_STAT(i, v) ((void)0)
+#endif
+
+template <int TPB>
+struct LaneRuns {  // one column per thread: conflict-free whatever row each lane is at
+    int s0[kLaneMaxRuns][TPB];
+    unsigned w[kLaneMaxRuns][TPB];  // gap2 (f32, low 12 mantissa bits dropped = rounded down) | run length
+};
+
+// scan this lane's listed runs; `bound` = f32 distance of a real candidate (or >= r2_ub): cells beyond its reach
+// cannot matter
+template <int TPB>
+__device__ __forceinline__ int scan_runs(const GridDev &G, const QueryCtx &c, int nruns, float bound, float r2_ub,
+                                         const LaneRuns<TPB> &L, Screen &r) {
+    const GridParams &g = G.p;
+    const float4 *__restrict__ hi = G.hi;
+    const int tid = threadIdx.x & (TPB - 1);
+    int ri = 0, s = 0, e = 0;
+    int steps = 0;  // dev statistics only; dead code otherwise
+    for (;;) {
+        if (s >= e) {  // next listed run (lanes that share cells get here together)
+            if (ri >= nruns) break;
+            const unsigned w = L.w[ri][tid];
+            s = L.s0[ri][tid];
+            e = s + (int)(w & kRunLenMask);
+            ++ri;
+            if (__uint_as_float(w & ~kRunLenMask) > reach_of(g, fminf(bound, r.best), r2_ub)) e = s;
+            continue;
+        }
+        // two candidates per step; the second is masked out when the run has one left
+        const bool two = s + 1 < e;
+        const float4 ta = __ldg(hi + s), tb = __ldg(hi + (two ? s + 1 : s));
+        const float ax = c.qx - ta.x, ay = c.qy - ta.y, az = c.qz - ta.z;
+        const float bx = c.qx - tb.x, by = c.qy - tb.y, bz = c.qz - tb.z;
+        const float da = fmaf(az, az, fmaf(ay, ay, ax * ax));
+        const float db = two ? fmaf(bz, bz, fmaf(by, by, bx * bx)) : 3.0e38f;
+        const float lo = fminf(da, db), hi2 = fmaxf(da, db);
+        const int slo = db < da ? s + 1 : s;
+        const bool lt = lo < r.best;
+        r.second = fminf(fminf(r.second, hi2), fmaxf(lo, r.best));
+        r.bs = lt ? slo : r.bs;
+        r.best = fminf(r.best, lo);
+        s += 2;
+        ++steps;
+    }
+    return steps;
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// list the occupied fine cells with done < gap2 <= thr (squared distance to the query) as runs, in ONE flat
+// loop over the cells of the query's box (nested loops with per-lane trip counts serialise: measured 30 passes of the inner body per warp
+// for 2.5 runs per lane).  Returns the number of runs, or kLaneMaxRuns + 1 when the lane must fall back.
+template <int TPB>
+__device__ __forceinline__ int list_runs(const GridDev &G, const QueryCtx &c, float thr, float done,
+                                         LaneRuns<TPB> &L) {
+    const GridParams &g = G.p;
+    const int tid = threadIdx.x & (TPB - 1);
+    const float fine2 = g.fine * g.fine;
+    // reach in fine cells.  The box must contain EVERY cell the deflated gap test below accepts (gap2 * 0.998
+    // <= thr, i.e. up to 1.001 x the reach): a later round skips cells with gap2 <= done as already scanned.
+    const float rho = sqrtf(thr) / g.fine * 1.0011f + 1e-4f;
+    const int x0 = max(c.gx - (int)ceilf(fmaxf(rho - c.fx, 0.0f)), 0),
+              x1 = min(c.gx + (int)ceilf(fmaxf(rho - (1.0f - c.fx), 0.0f)), g.fdim[0] - 1);
+    const int y0 = max(c.gy - (int)ceilf(fmaxf(rho - c.fy, 0.0f)), 0),
+              y1 = min(c.gy + (int)ceilf(fmaxf(rho - (1.0f - c.fy), 0.0f)), g.fdim[1] - 1);
+    const int z0 = max(c.gz - (int)ceilf(fmaxf(rho - c.fz, 0.0f)), 0),
+              z1 = min(c.gz + (int)ceilf(fmaxf(rho - (1.0f - c.fz), 0.0f)), g.fdim[2] - 1);
+    int n = 0;
+    int x = x0, y = y0, z = z0;
+    // cell offsets from the home cell as floats, stepped with the integers (no conversions in the loop)
+    const float ox0 = (float)(x0 - c.gx), oy0 = (float)(y0 - c.gy);
+    float ox = ox0, oy = oy0, oz = (float)(z0 - c.gz);
+    for (;;) {
+        // squared distance from the query to cell (x, y, z), deflated: never drop a cell that could matter
+        const float ex = fmaxf(fmaxf(ox - c.fx, c.fx - ox - 1.0f), 0.0f);
+        const float ey = fmaxf(fmaxf(oy - c.fy, c.fy - oy - 1.0f), 0.0f);
+        const float ez = fmaxf(fmaxf(oz - c.fz, c.fz - oz - 1.0f), 0.0f);
+        const float gap2 = fmaxf((ex * ex + ey * ey + ez * ez) * fine2 * 0.998f - 1e-12f * fine2, 0.0f);
+        if (gap2 <= thr && gap2 > done) {
+            const CoarseCell cc = G.coarse[((z >> 2) * g.cdim[1] + (y >> 2)) * g.cdim[0] + (x >> 2)];
+            const int bit = (x & 3) + 4 * (y & 3) + 16 * (z & 3);
+            if ((cc.mask >> bit) & 1ull) {
+                const int rank = __popcll(cc.mask & ((1ull << bit) - 1ull));
+                const int s0 = __ldg(G.fstart + cc.base + rank), s1 = __ldg(G.fstart + cc.base + rank + 1);
+                if (n >= kLaneMaxRuns || s1 - s0 > (int)kRunLenMask) {
+                    n = kLaneMaxRuns + 1;  // fall back; the remaining cells are skipped by the test below
+                    z = z1; y = y1; x = x1;
+                } else {
+                    prefetch_l1(G.hi + s0);
+                    L.s0[n][tid] = s0;
+                    L.w[n][tid] = (__float_as_uint(gap2) & ~kRunLenMask) | (unsigned)(s1 - s0);
+                    ++n;
+                }
+            }
+        }
+        // step (x, y, z) through the box with selects only: one backward branch, so the lanes of a warp stay
+        // converged for max(box volume) trips
+        const bool wx = x == x1, wy = wx && y == y1;
+        x = wx ? x0 : x + 1;
+        ox = wx ? ox0 : ox + 1.0f;
+        y = wy ? y0 : (wx ? y + 1 : y);
+        oy = wy ? oy0 : (wx ? oy + 1.0f : oy);
+        z += wy ? 1 : 0;
+        oz += wy ? 1.0f : 0.0f;
+        if (z > z1) break;
+    }
+    return n;
+}
+
+// All 32 lanes of the warp must call this together.  `prior` = sorted position of a target point believed to
+// be close to the query (or -1): only ever used as an upper bound, never as an answer.
+template <int TPB>
+__device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, const QueryCtx &c, double qx, double qy,
+                                                double qz, double r2, float r2_ub, int prior, LaneRuns<TPB> &L,
+                                                double *d2_out) {
+    const unsigned FULL = 0xffffffffu;
+    static_assert((TPB & (TPB - 1)) == 0, "TPB must be a power of two");
+    const GridParams &g = G.p;
+    enum { kDone = 0, kScan = 1, kCoop = 2 };
+    Screen r;
+    r.best = r2_ub; r.second = 3.0e38f; r.bs = -1;
+    const float max_reach2 = (kLaneMaxRho * g.fine) * (kLaneMaxRho * g.fine);
+    float bound = r2_ub;  // f32 distance of a real candidate, when one is known
+    float thr = (kLaneProbeRho * g.fine) * (kLaneProbeRho * g.fine);  // no bound yet: probe the nearest cells
+    int mode = valid ? kScan : kDone;
+    if (valid && prior >= 0) {
+        const float4 t = __ldg(G.hi + prior);
+        const float dx = c.qx - t.x, dy = c.qy - t.y, dz = c.qz - t.z;
+        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d < r2_ub) {
+            bound = d;
+            thr = reach_of(g, bound, r2_ub);
+            if (thr > max_reach2) { mode = kCoop; VB_STAT(4, 1); }
+        }
+    }
+    VB_STAT(0, valid);
+    VB_STAT(1, bound < r2_ub);
+    if ((threadIdx.x & 31) == 0) VB_STAT(11, 1);
+    float done = -1.0f;  // every cell with gap2 <= done has been scanned
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+        int nruns = 0, steps = 0;
+        if (mode == kScan) {
+            nruns = list_runs<TPB>(G, c, thr, done, L);
+            if (nruns > kLaneMaxRuns) {
+                mode = kCoop;
+                VB_STAT(5, 1);
+            } else {
+                VB_STAT(7, nruns);
+                steps = scan_runs<TPB>(G, c, nruns, bound, r2_ub, L, r);
+                done = thr;
+                if (r.bs >= 0) {
+                    // complete once the reach of the final best lies inside what has been scanned
+                    const float need = reach_of(g, fminf(bound, r.best), r2_ub);
+                    if (need <= done) mode = kDone;
+                    else if (need <= max_reach2) thr = need;
+                    else { mode = kCoop; VB_STAT(4, 1); }
+                } else if (done < max_reach2) {
+                    thr = max_reach2;  // nothing within the probe: everything this path may search
+                } else {
+                    mode = kCoop;
+                    VB_STAT(6, 1);
+                }
+            }
+        }
+#ifdef VB_STATS
+        VB_STAT(8, steps);
+        {
+            const int mx = __reduce_max_sync(FULL, steps);
+            if ((threadIdx.x & 31) == 0) VB_STAT(9, mx);
+        }
+#else
+        (void)steps;
+#endif
+        if (!__any_sync(FULL, mode == kScan)) break;
+    }
+    if (mode == kScan) mode = kCoop;  // still open after two rounds
+    const unsigned coop = __ballot_sync(FULL, mode == kCoop);
+    VB_STAT(3, mode == kCoop);
+    if (coop && (threadIdx.x & 31) == 0) VB_STAT(10, 1);
+    if (coop) {
+        const Screen rc = coop_screen(G, coop, c, r2_ub);
+        if (mode == kCoop) r = rc;
+    }
+    *d2_out = 0.0;
+    if (!valid) return -1;
+    return nn_decide(G, r, c, qx, qy, qz, r2, r2_ub, d2_out);
 }
 
 // ---- warp-per-query search --------------------------------------------------------------------------------

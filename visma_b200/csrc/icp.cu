@@ -40,7 +40,10 @@ namespace {
 #endif
 constexpr int kPassTpb = VB_PASS_TPB;
 constexpr int kPassWarps = kPassTpb / 32;  // every warp writes its own partial: no block-level barrier
-constexpr int kPtsPerThread = 4;
+#ifndef VB_PASS_PTS
+#define VB_PASS_PTS 4
+#endif
+constexpr int kPtsPerThread = VB_PASS_PTS;
 constexpr int kChunk = kPassTpb * kPtsPerThread;  // source points per block
 constexpr int kAcc = 32;                          // accumulator slots (padded)
 constexpr int kBuckets = 32768;                   // spatial buckets per source cloud (15-bit key)
@@ -134,62 +137,134 @@ __device__ __forceinline__ void contributions(bool matched, double d2, const dou
     v[kSlotCount] = 1.0;
 }
 
+// per-warp shared scratch: the search's run lists, then the estimator rows (never live at the same time)
+constexpr int kRowStride = 10;  // doubles per staged row: 80 B keeps the 16-byte row stores conflict-free
+struct __align__(16) WarpScratch {
+    union {
+        LaneRuns<32> runs;
+        double rows[32 * kRowStride];
+    };
+};
+constexpr int kPart = 64;  // doubles per warp partial: the 8x8 Gram matrix of the staged rows
+
+// D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor cores (DMMA).  Lane l holds A[l>>2][l&3], B[l&3][l>>2] and
+// D[l>>2][2(l&3) + {0,1}].
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
 // One ICP correspondence pass for every active problem: transform + radius-bounded 1-NN + estimator
-// products + block reduction.  grid = one block per kChunk source points of one problem.
+// products + reduction.  grid = one block per kChunk source points of one problem.
+//
+// Estimator sums: every matched lane stages one row x of 8 doubles — point-to-plane [J (6), r, 0] with
+// r = (vs - vt).nt, J = [vs x nt ; nt] (TransformationEstimation.cpp:87-89); point-to-point
+// [s' (3), d' (3), 1, 0] with (s', d') = (vs - c, vt - c) — and the warp accumulates the Gram matrix
+// sum_i x_i x_i^T with 8 DMMA instructions per 32 points: JTJ = D[0..5][0..5], JTr = D[0..5][6]
+// (resp. the umeyama moments sum d' s'^T = D[3..5][0..2], sum s' = D[0..2][6], sum d' = D[3..5][6]).  The
+// accumulator fragment lives in two registers per lane across the warp's batches.  (The first version
+// formed 27 products per lane and reduced 32 slots with a 31-step shuffle tree: ~280 instructions and 64
+// live registers per batch.)
 template <int MODE>
 __global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass(GridDev G, const double *__restrict__ src_xyz,
                                                    const BlockTask *__restrict__ tasks,
                                                    const ProbState *__restrict__ states,
-                                                   double *__restrict__ partials, int *__restrict__ corr_j,
+                                                   double *__restrict__ partials, int *__restrict__ corr_s,
                                                    PassParams pp) {
     const BlockTask task = tasks[blockIdx.x];
     const ProbState *st = states + task.prob;
     if (st->done) return;
+    __shared__ WarpScratch scratch[kPassWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double T[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) T[i] = st->T[i];  // warp-uniform broadcast loads
-    // cref = translation part of T: keeps the p2p moments O(object size) instead of O(scene size)
-    const double cref[3] = {T[3], T[7], T[11]};
-    double acc = 0.0;  // lane L accumulates slot L
+    WarpScratch &ws = scratch[warp];
+    double c0 = 0.0, c1 = 0.0;  // this lane's two entries of the warp's Gram matrix
+    double sum_d2 = 0.0;        // exact NN distances (Registration.cpp:68), warp total in every lane
+    int count = 0;
 #pragma unroll 1
     for (int k = 0; k < kPtsPerThread; k++) {
         // a warp owns kPtsPerThread consecutive batches of 32 consecutive (spatially sorted) points
         const int local = (warp * kPtsPerThread + k) * 32 + lane;
         const bool valid = local < task.count;
-        bool matched = false;
-        double d2 = 0.0, vs[3] = {0, 0, 0}, vt[3] = {0, 0, 0}, nt[3] = {0, 0, 0};
+        double d2 = 0.0, vs[3] = {0, 0, 0};
         QueryCtx c;
         bool inside = false;
+        int prior = -1;
         if (valid) {
+            prior = corr_s[task.corr_begin + local];  // last iteration's match: a bound for this one
+#ifndef VB_NO_PRIOR_PREFETCH
+            if (prior >= 0) {
+                // most likely the match again: have its exact point / normal in L1 by the time the decision needs them
+                prefetch_l1(G.xyz + 3 * (int64_t)prior);
+                if (MODE == 1) prefetch_l1(G.nrm + 3 * (int64_t)prior);
+            }
+#endif
             const double *p = src_xyz + 3 * (int64_t)(task.src_begin + local);
             const double px = p[0], py = p[1], pz = p[2];
+            const double *T = st->T;  // warp-uniform broadcast loads (not held in registers across the search)
             vs[0] = T[0] * px + T[1] * py + T[2] * pz + T[3];
             vs[1] = T[4] * px + T[5] * py + T[6] * pz + T[7];
             vs[2] = T[8] * px + T[9] * py + T[10] * pz + T[11];
             inside = make_query(G.p, vs[0], vs[1], vs[2], c);
         }
-        // warp-cooperative search: every lane takes part, lanes without a query just ride along
+        // every lane takes part in the search, lanes without a query just ride along
+#ifdef VB_SEARCH_COOP_ONLY
+        (void)prior;
         const int bs = nn_search_warp(G, inside, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, &d2);
-        matched = bs >= 0;
+#else
+        const int bs = nn_search_hybrid<32>(G, inside, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, prior, ws.runs, &d2);
+#endif
+        const bool matched = bs >= 0;
+        double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (valid) {
-            int j = -1;
             if (matched) {
-                j = __ldg(G.orig + bs);
                 const double *t = G.xyz + 3 * (int64_t)bs;
-                vt[0] = t[0]; vt[1] = t[1]; vt[2] = t[2];
+                const double vt[3] = {t[0], t[1], t[2]};
                 if (MODE == 1) {
                     const double *nn = G.nrm + 3 * (int64_t)bs;
-                    nt[0] = nn[0]; nt[1] = nn[1]; nt[2] = nn[2];
+                    const double nt[3] = {nn[0], nn[1], nn[2]};
+                    x[0] = vs[1] * nt[2] - vs[2] * nt[1];
+                    x[1] = vs[2] * nt[0] - vs[0] * nt[2];
+                    x[2] = vs[0] * nt[1] - vs[1] * nt[0];
+                    x[3] = nt[0]; x[4] = nt[1]; x[5] = nt[2];
+                    x[6] = (vs[0] - vt[0]) * nt[0] + (vs[1] - vt[1]) * nt[1] + (vs[2] - vt[2]) * nt[2];
+                } else {
+                    // cref = translation part of T: keeps the moments O(object size) instead of O(scene size)
+                    const double cr[3] = {st->T[3], st->T[7], st->T[11]};
+                    x[0] = vs[0] - cr[0]; x[1] = vs[1] - cr[1]; x[2] = vs[2] - cr[2];
+                    x[3] = vt[0] - cr[0]; x[4] = vt[1] - cr[1]; x[5] = vt[2] - cr[2];
+                    x[6] = 1.0;
                 }
             }
-            corr_j[task.corr_begin + local] = j;
+            corr_s[task.corr_begin + local] = bs;  // sorted position; vb200_batch_corr maps it to the caller's index
         }
-        double v[kAcc];
-        contributions<MODE>(matched, d2, vs, vt, nt, cref, v);
-        acc += warp_reduce_slots(v);
+        __syncwarp();  // the run lists are dead: the scratch now holds the estimator rows
+        {
+            double2 *row = reinterpret_cast<double2 *>(ws.rows + lane * kRowStride);
+            row[0] = make_double2(x[0], x[1]);
+            row[1] = make_double2(x[2], x[3]);
+            row[2] = make_double2(x[4], x[5]);
+            row[3] = make_double2(x[6], x[7]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) {
+            const double a = ws.rows[(4 * ch + (lane & 3)) * kRowStride + (lane >> 2)];
+            dmma_m8n8k4(c0, c1, a, a);
+        }
+        // sum of exact NN distances and the inlier count (fixed-order butterfly: deterministic)
+        double dd = matched ? d2 : 0.0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+        sum_d2 += dd;
+        count += __popc(__ballot_sync(0xffffffffu, matched));
+        __syncwarp();  // rows consumed before the next batch lists its runs
     }
-    partials[((int64_t)blockIdx.x * kPassWarps + warp) * kAcc + lane] = acc;  // one coalesced 256-byte row per warp
+    // D[l>>2][2(l&3) + {0,1}] = entries 2l, 2l+1 of the row-major 8x8: one coalesced 512-byte row per warp.
+    // Row 7 of D is identically zero (x[7] = 0); its last two entries carry the count and sum d2.
+    if (lane == 31) { c0 = (double)count; c1 = sum_d2; }
+    double2 *out = reinterpret_cast<double2 *>(partials + ((int64_t)blockIdx.x * kPassWarps + warp) * kPart);
+    out[lane] = make_double2(c0, c1);
 }
 
 // ---- estimator solves from the reduced slots ---------------------------------------------------------
@@ -239,21 +314,41 @@ __device__ void update_p2p(const double *tot, const double *cref, double *U) {
     }
 }
 
-// One block per problem: fixed-order reduction of the pass partials, result bookkeeping, convergence test
-// (Registration.cpp:179-183) and the estimator update T <- update * T (Registration.cpp:172-174).
-// fixed-order reduction of one problem's per-warp partials into tot[kAcc] (shared memory); 256 threads
-__device__ __forceinline__ void reduce_partials(const ProbDesc &pd, const double *__restrict__ partials,
-                                                double (*sw)[kAcc], double *tot) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Fixed-order reduction of one problem's per-warp partials (8x8 Gram matrices, kPart doubles each) into the
+// 32 estimator slots tot[kAcc] (shared memory); 256 threads.  Slot layout: point-to-plane 0..20 JTJ upper
+// triangle row-major, 21..26 JTr; point-to-point 0..2 sum s', 3..5 sum d', 6..14 sum d' s'^T, 15 sum |s'|^2;
+// both 30 = sum d2, 31 = count.
+__device__ __forceinline__ void reduce_partials(const ProbDesc &pd, const double *__restrict__ partials, bool plane,
+                                                double (*sw)[kPart], double *tot) {
+    const int e = threadIdx.x & (kPart - 1), grp = threadIdx.x / kPart;  // 4 groups of 64 threads
     double s = 0.0;
-    for (int b = warp; b < pd.blk_count * kPassWarps; b += 8)
-        s += partials[((int64_t)pd.blk_begin * kPassWarps + b) * kAcc + lane];
-    sw[warp][lane] = s;
+    for (int b = grp; b < pd.blk_count * kPassWarps; b += 4)
+        s += partials[((int64_t)pd.blk_begin * kPassWarps + b) * kPart + e];
+    sw[grp][e] = s;
+    __syncthreads();
+    if (threadIdx.x < kPart) sw[0][e] = ((sw[0][e] + sw[1][e]) + sw[2][e]) + sw[3][e];
     __syncthreads();
     if (threadIdx.x < kAcc) {
-        double t = sw[0][threadIdx.x];
-        for (int w = 1; w < 8; w++) t += sw[w][threadIdx.x];
-        tot[threadIdx.x] = t;
+        const double *D = sw[0];
+        const int t = threadIdx.x;
+        double v = 0.0;
+        if (t == kSlotD2) v = D[63];
+        else if (t == kSlotCount) v = D[62];
+        else if (plane) {
+            if (t < 21) {
+                int a = 0, rem = t;
+                while (rem >= 6 - a) { rem -= 6 - a; ++a; }  // slot t = (a, b) of the upper triangle, b >= a
+                v = D[8 * a + a + rem];
+            } else if (t < 27) {
+                v = D[8 * (t - 21) + 6];
+            }
+        } else {
+            if (t < 3) v = D[8 * t + 6];
+            else if (t < 6) v = D[8 * t + 6];
+            else if (t < 15) v = D[8 * (3 + (t - 6) / 3) + (t - 6) % 3];
+            else if (t == 15) v = (D[0] + D[9]) + D[18];
+        }
+        tot[t] = v;
     }
     __syncthreads();
 }
@@ -301,9 +396,9 @@ __global__ void __launch_bounds__(256) k_solve(const ProbDesc *__restrict__ prob
     const ProbDesc pd = probs[blockIdx.x];
     ProbState *st = states + blockIdx.x;
     if (st->done) return;
-    __shared__ double sw[8][kAcc];
+    __shared__ double sw[4][kPart];
     __shared__ double tot[kAcc];
-    reduce_partials(pd, partials, sw, tot);
+    reduce_partials(pd, partials, sp.estimator != VB200_EST_P2P, sw, tot);
     if (threadIdx.x == 0) solve_from_totals(tot, (double)pd.npts, st, sp, pass_index);
 }
 
@@ -312,14 +407,15 @@ __global__ void __launch_bounds__(256) k_solve(const ProbDesc *__restrict__ prob
 // caller all-reduces across GPUs, k_solve_totals finishes the iteration from the combined totals.  Every rank
 // sees identical totals, hence applies the identical update: no broadcast of T is needed.
 __global__ void __launch_bounds__(256) k_reduce(const ProbDesc *__restrict__ probs, const ProbState *__restrict__ states,
-                                                const double *__restrict__ partials, double *__restrict__ totals) {
+                                                const double *__restrict__ partials, bool plane,
+                                                double *__restrict__ totals) {
     const ProbDesc pd = probs[blockIdx.x];
-    __shared__ double sw[8][kAcc];
+    __shared__ double sw[4][kPart];
     __shared__ double tot[kAcc];
     if (states[blockIdx.x].done) {  // finished problems contribute their last totals unchanged
         return;
     }
-    reduce_partials(pd, partials, sw, tot);
+    reduce_partials(pd, partials, plane, sw, tot);
     if (threadIdx.x < kAcc) totals[(int64_t)blockIdx.x * kAcc + threadIdx.x] = tot[threadIdx.x];
 }
 
@@ -397,6 +493,16 @@ __global__ void __launch_bounds__(256) k_src_gather(const double *__restrict__ i
     out[3 * (int64_t)s + 1] = in[3 * (int64_t)i + 1];
     out[3 * (int64_t)s + 2] = in[3 * (int64_t)i + 2];
     orig[s] = i - cloud_off[find_cloud(cloud_off, ncloud, i)];
+}
+
+// correspondences are kept as sorted scene positions (they double as the next pass's search bound); this maps
+// one problem's column to the caller's target indices
+__global__ void __launch_bounds__(256) k_corr_orig(const int *__restrict__ corr_s, int n, const int *__restrict__ orig,
+                                                   int *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = corr_s[i];
+    out[i] = s >= 0 ? orig[s] : -1;
 }
 
 // ---- estimator plug-in kernel: reductions over an explicit correspondence list ------------------------
@@ -595,7 +701,7 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
     VB_CUDA(cudaMallocAsync((void **)&b->d_probs, sizeof(ProbDesc) * (size_t)std::max(P, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_states, sizeof(ProbState) * (size_t)std::max(P, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_tasks, sizeof(BlockTask) * (size_t)std::max(b->nblk, 1), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_partials, sizeof(double) * kAcc * kPassWarps * (size_t)std::max(b->nblk, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_partials, sizeof(double) * kPart * kPassWarps * (size_t)std::max(b->nblk, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_corr, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
     if (P) {
         VB_CUDA(cudaMemcpyAsync(b->d_probs, b->probs.data(), sizeof(ProbDesc) * (size_t)P, cudaMemcpyHostToDevice, st));
@@ -687,7 +793,7 @@ static int batch_pass(Batch *b, int estimator, double max_dist) {
             k_pass<0><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
         b->launches++;
     }
-    k_reduce<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, totals);
+    k_reduce<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, estimator != VB200_EST_P2P, totals);
     b->launches++;
     VB_CUDA(cudaGetLastError());
     return VB200_OK;
@@ -890,8 +996,13 @@ extern "C" int vb200_batch_corr(vb200_batch_t *batch, int32_t p, int32_t *out_co
     VB_CUDA(cudaSetDevice(b->scene->device));
     const vb::ProbDesc &pd = b->probs[p];
     std::vector<int> cj((size_t)pd.npts), so((size_t)pd.npts);
+    vb::DevBuf<int> d_j(b->scene->stream);
     if (pd.npts) {
-        VB_CUDA(cudaMemcpyAsync(cj.data(), b->d_corr + pd.corr_begin, sizeof(int) * (size_t)pd.npts,
+        VB_CUDA(d_j.alloc((size_t)pd.npts));
+        vb::k_corr_orig<<<vb::div_up(pd.npts, 256), 256, 0, b->scene->stream>>>(b->d_corr + pd.corr_begin, pd.npts,
+                                                                               b->scene->grid.orig, d_j.p);
+        VB_CUDA(cudaGetLastError());
+        VB_CUDA(cudaMemcpyAsync(cj.data(), d_j.p, sizeof(int) * (size_t)pd.npts,
                                 cudaMemcpyDeviceToHost, b->scene->stream));
         VB_CUDA(cudaMemcpyAsync(so.data(), b->d_src_orig + pd.src_begin, sizeof(int) * (size_t)pd.npts,
                                 cudaMemcpyDeviceToHost, b->scene->stream));
@@ -1039,3 +1150,15 @@ extern "C" int vb200_estimate(const double *src_xyz, int64_t m, const double *tg
     VB_CUDA(cudaMemcpy(out_T, d_T.p, sizeof(double) * 16, cudaMemcpyDeviceToHost));
     return VB200_OK;
 }
+
+#ifdef VB_STATS
+// dev builds only (scripts/build_variants.sh ... "-DVB_STATS"): search-path counters of grid.cuh
+extern "C" int vb200_debug_stats(unsigned long long *out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, vb::g_stats, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(vb::g_stats, z, sizeof(z));
+    }
+    return 0;
+}
+#endif

@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(kTpb) k_knn1(GridDev G, const double *__restri
         x = q[3 * i]; y = q[3 * i + 1]; z = q[3 * i + 2];
         inside = make_query(G.p, x, y, z, c);
     }
-    const int bs = nn_search_warp(G, inside, c, x, y, z, r2, r2_ub, &d2);
+    __shared__ LaneRuns<kTpb> runs;
+    const int bs = nn_search_hybrid<kTpb>(G, inside, c, x, y, z, r2, r2_ub, -1, runs, &d2);
     if (live) {
         out_idx[i] = bs >= 0 ? __ldg(G.orig + bs) : -1;
         out_d2[i] = bs >= 0 ? d2 : 0.0;
