@@ -329,6 +329,7 @@ def run_ours(args):
                        "back_to_back_ms_per_iteration_no_flush": loop_ms,
                        "pass_ms": p_ms, "pass_ms_first3": [round(float(x), 4) for x in pass_ms[:3]],
                        "pass_ms_last3": [round(float(x), 4) for x in pass_ms[-3:]],
+                       "pass_ms_per_step": [round(float(x), 3) for x in pass_ms],
                        "solve_ms": float(np.mean(solve_ms)), "allgather_ms": ag_ms,
                        "scene_build_s": scene_build_s, "converged_to_ground_truth": ok,
                        "max_pose_err_rad_m": [float(errs[:, 0].max()), float(errs[:, 1].max())]},

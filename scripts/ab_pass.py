@@ -6,6 +6,6 @@ for lib in sys.argv[1:]:
                          env=env, capture_output=True, text=True)
     try:
         j = json.loads(out.stdout.strip().splitlines()[-1])
-        print(lib, os.environ.get("VB200_CELL_SCALE", ""), "pass_ms %.4f" % j["config"]["pass_ms"], j["config"].get("pass_ms_first3"), j["config"].get("pass_ms_last3"), "value %.1f" % j["value"], "e2e %.1f" % j["e2e"]["value"], j["e2e"]["note"])
+        print(lib, os.environ.get("VB200_CELL_SCALE", ""), "pass_ms %.4f" % j["config"]["pass_ms"], j["config"].get("pass_ms_first3"), j["config"].get("pass_ms_last3"), "value %.1f" % j["value"], "e2e %.1f" % j["e2e"]["value"], j["e2e"]["note"], j["config"].get("pass_ms_per_step"))
     except Exception as e:
         print(lib, "FAILED", out.stdout[-500:], out.stderr[-1500:])

@@ -9,7 +9,8 @@ if sys.argv[1] == "--cmp":
     a, b = np.load(sys.argv[2]), np.load(sys.argv[3])
     bad = 0
     for k in a.files:
-        same = np.array_equal(a[k], b[k])
+        # correspondences must be identical; poses / rmse may differ in the last bits (summation grouping)
+        same = np.array_equal(a[k], b[k]) if "corr" in k else np.allclose(a[k], b[k], rtol=1e-9, atol=1e-12)
         if not same:
             bad += 1
             d = a[k] != b[k]

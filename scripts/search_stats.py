@@ -14,7 +14,7 @@ L.vb200_debug_stats.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
 buf = (C.c_ulonglong * 16)()
 L.vb200_debug_stats(None, 1)
 names = ["valid", "prior", "", "coop", "coop:reach", "coop:overflow", "coop:nohome", "runs", "lane_steps", "warp_max_steps",
-         "warps_w_coop", "warps"]
+         "warps_w_coop", "warps", "hard", "hard:noprior", "hard:nosec"]
 est = reg.TransformationEstimationPointToPlane()
 for it in range(n_iter):
     batch.iterate(est, 0.075, 1)

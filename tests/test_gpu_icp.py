@@ -264,3 +264,68 @@ def test_split_iteration_equals_fused(vb, scene, name):
     assert np.allclose(ra.transformation_, whole.transformation_, atol=1e-9, rtol=0)
     assert abs(ra.fitness_ - whole.fitness_) <= 1.0 / len(src) and abs(ra.inlier_rmse_ - whole.inlier_rmse_) < 1e-9
     assert ra.iterations_ == whole.iterations_
+
+
+@pytest.mark.parametrize("name", ["p2p", "p2plane"])
+def test_cached_neighbours_equal_fresh_search(vb, scene, name):
+    """k_pass keeps, per source point, what its last search proved and skips the search while the triangle
+    inequality shows the neighbour unchanged.  That must be invisible: after every iteration of a running
+    batch the correspondences equal those of a FRESH batch (no history) evaluated at the same transforms,
+    and they equal the independent warp-per-query KNN of the transformed points."""
+    est = {"p2p": vb.reg.TransformationEstimationPointToPoint(),
+           "p2plane": vb.reg.TransformationEstimationPointToPlane()}[name]
+    sc = vb.reg.Scene(vb.reg.PointCloud(scene["scene_xyz"], scene["scene_nrm"]), 0.075)
+    cl = clouds(vb, scene)
+    run = vb.reg.Batch(sc, cl)
+    run.set_problems(scene["T_init"])
+    T = np.array(scene["T_init"], dtype=np.float64)
+    for it in range(14):
+        run.iterate(est, 0.075, 1)          # pass at T (cache from the previous iterations), then T <- update * T
+        got = run.results(want_corr=True)
+        fresh = vb.reg.Batch(sc, cl)
+        fresh.set_problems(T)
+        fresh.iterate(est, 0.075, 1)
+        want = fresh.results(want_corr=True)
+        for b, (g, w) in enumerate(zip(got, want)):
+            assert np.array_equal(g.correspondence_set_, w.correspondence_set_), (it, b)
+            assert np.allclose(g.transformation_, w.transformation_, rtol=1e-12, atol=1e-14)
+            assert abs(g.inlier_rmse_ - w.inlier_rmse_) < 1e-13
+        if it in (0, 5, 13):
+            # the other search kernel (one warp per query, no history) on the same transformed points
+            for b in (0, len(cl) - 1):
+                q = cl[b].points_ @ T[b][:3, :3].T + T[b][:3, 3]
+                idx, _ = sc.SearchHybrid1(q[:3000], 0.075)
+                full = -np.ones(len(q), np.int64)
+                cs = got[b].correspondence_set_
+                full[cs[:, 0]] = cs[:, 1]
+                assert np.array_equal(full[:3000], idx), (it, b)
+        T = np.stack([r.transformation_ for r in got])
+        fresh.close()
+
+
+def test_cache_survives_set_problems_and_tiny_moves(vb, scene):
+    """set_problems() forgets the history; a transform nudged by less than the search slack re-uses it.  Either
+    way the answer is that of a fresh search."""
+    est = vb.reg.TransformationEstimationPointToPlane()
+    sc = vb.reg.Scene(vb.reg.PointCloud(scene["scene_xyz"], scene["scene_nrm"]), 0.075)
+    cl = clouds(vb, scene)
+    b1 = vb.reg.Batch(sc, cl)
+    b1.set_problems(scene["T_init"])
+    b1.iterate(est, 0.075, 12)
+    T12 = np.stack([r.transformation_ for r in b1.results()])
+    nudged = T12.copy()
+    nudged[:, :3, 3] += 2e-4       # 0.2 mm: inside the slack, most points keep their cached neighbour
+    for T in (T12, nudged, scene["T_init"]):
+        b1.set_problems(T)
+        # warm the history at T, then evaluate once more at the resulting transform
+        b1.iterate(est, 0.075, 1)
+        Tn = np.stack([r.transformation_ for r in b1.results()])
+        b1.iterate(est, 0.075, 1)
+        got = b1.results(want_corr=True)
+        b2 = vb.reg.Batch(sc, cl)
+        b2.set_problems(Tn)
+        b2.iterate(est, 0.075, 1)
+        want = b2.results(want_corr=True)
+        for g, w in zip(got, want):
+            assert np.array_equal(g.correspondence_set_, w.correspondence_set_)
+        b2.close()

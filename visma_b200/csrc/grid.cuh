@@ -468,12 +468,14 @@ __device__ __forceinline__ Screen coop_screen(const GridDev &G, unsigned pending
 // The decision in double from a completed f32 screening (per lane): the winner's exact d2 against the
 // reference's threshold, or the double re-walk when the f32 result is ambiguous.
 __device__ __forceinline__ int nn_decide(const GridDev &G, const Screen &r, const QueryCtx &c, double qx, double qy,
-                                         double qz, double r2, float r2_ub, double *d2_out) {
+                                         double qz, double r2, float r2_ub, double *d2_out, bool *unique = nullptr) {
     const GridParams &g = G.p;
     *d2_out = 0.0;
+    if (unique) *unique = false;
     if (r.bs < 0) return -1;
     const float bb = band(g, r.best);
     if (r.second - r.best > bb + band(g, r.second)) {
+        if (unique) *unique = true;  // r.bs is the true nearest: every other point is farther even in double
         const double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)r.bs);
         if (d < r2) { *d2_out = d; return r.bs; }
         return -1;
@@ -513,6 +515,10 @@ constexpr float kLaneMaxRho = VB_LANE_MAX_RHO_PCT * 0.01f;  // largest reach (fi
 #define VB_LANE_PROBE_RHO_PCT 50
 #endif
 constexpr float kLaneProbeRho = VB_LANE_PROBE_RHO_PCT * 0.01f;  // first reach of a lane that has no bound yet
+#ifndef VB_BIG_RHO_PCT
+#define VB_BIG_RHO_PCT 75
+#endif
+constexpr float kLaneBigRho = VB_BIG_RHO_PCT * 0.01f;  // a reach beyond this counts towards sending the warp to the shared walk
 constexpr unsigned kRunLenBits = 12, kRunLenMask = (1u << kRunLenBits) - 1u;
 
 #ifdef VB_STATS
@@ -521,6 +527,12 @@ __device__ unsigned long long g_stats[16];
 #else
 #define VB_STAT(i, v) ((void)0)
 #endif
+
+// (sqrt(thr) + slack)^2, capped — never below thr itself
+__device__ __forceinline__ float widen(float thr, float slack, float cap) {
+    const float s = sqrtf(thr) + slack;
+    return fmaxf(thr, fminf(s * s, cap));
+}
 
 template <int TPB>
 struct LaneRuns {  // one column per thread: conflict-free whatever row each lane is at
@@ -532,7 +544,7 @@ struct LaneRuns {  // one column per thread: conflict-free whatever row each lan
 // cannot matter
 template <int TPB>
 __device__ __forceinline__ int scan_runs(const GridDev &G, const QueryCtx &c, int nruns, float bound, float r2_ub,
-                                         const LaneRuns<TPB> &L, Screen &r) {
+                                         float slack, float cap, const LaneRuns<TPB> &L, Screen &r) {
     const GridParams &g = G.p;
     const float4 *__restrict__ hi = G.hi;
     const int tid = threadIdx.x & (TPB - 1);
@@ -545,7 +557,9 @@ __device__ __forceinline__ int scan_runs(const GridDev &G, const QueryCtx &c, in
             s = L.s0[ri][tid];
             e = s + (int)(w & kRunLenMask);
             ++ri;
-            if (__uint_as_float(w & ~kRunLenMask) > reach_of(g, fminf(bound, r.best), r2_ub)) e = s;
+            // a listed run is dropped only when it lies beyond the (widened) reach of the best so far: every
+            // cell within widen(reach_of(final best)) is therefore scanned (nn_search_hybrid's `cover`)
+            if (__uint_as_float(w & ~kRunLenMask) > widen(reach_of(g, fminf(bound, r.best), r2_ub), slack, cap)) e = s;
             continue;
         }
         // two candidates per step; the second is masked out when the run has one left
@@ -631,10 +645,17 @@ __device__ __forceinline__ int list_runs(const GridDev &G, const QueryCtx &c, fl
 
 // All 32 lanes of the warp must call this together.  `prior` = sorted position of a target point believed to
 // be close to the query (or -1): only ever used as an upper bound, never as an answer.
+//
+// `slack` (metric, >= 0) widens every lane-private search beyond what the answer needs, and *sec_out (nullable)
+// receives a lower bound of the TRUE squared distance from the query to every target point other than the
+// returned one (or a negative value when no such statement can be made): the caller keeps it with the query
+// position and can later prove, by the triangle inequality, that the answer is unchanged after a small move
+// (k_pass: Greenspan & Godin's cached-neighbour test for ICP).
 template <int TPB>
 __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, const QueryCtx &c, double qx, double qy,
                                                 double qz, double r2, float r2_ub, int prior, LaneRuns<TPB> &L,
-                                                double *d2_out) {
+                                                double *d2_out, float slack = 0.0f, float *sec_out = nullptr,
+                                                int coop_lanes = 32) {
     const unsigned FULL = 0xffffffffu;
     static_assert((TPB & (TPB - 1)) == 0, "TPB must be a power of two");
     const GridParams &g = G.p;
@@ -653,7 +674,15 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
             bound = d;
             thr = reach_of(g, bound, r2_ub);
             if (thr > max_reach2) { mode = kCoop; VB_STAT(4, 1); }
+            else thr = widen(thr, slack, max_reach2);
         }
+    }
+    if (coop_lanes < 32) {
+        // a warp most of whose lanes have a long reach (the first iterations of an alignment) is better served
+        // by the shared walk: long reaches overlap, and listing big boxes lane by lane is what costs
+        const float big2 = (kLaneBigRho * g.fine) * (kLaneBigRho * g.fine);
+        const bool big = mode == kCoop || (mode == kScan && (bound >= r2_ub || thr > big2));
+        if (__popc(__ballot_sync(FULL, big)) > coop_lanes && mode == kScan) mode = kCoop;
     }
     VB_STAT(0, valid);
     VB_STAT(1, bound < r2_ub);
@@ -669,13 +698,13 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
                 VB_STAT(5, 1);
             } else {
                 VB_STAT(7, nruns);
-                steps = scan_runs<TPB>(G, c, nruns, bound, r2_ub, L, r);
+                steps = scan_runs<TPB>(G, c, nruns, bound, r2_ub, slack, max_reach2, L, r);
                 done = thr;
                 if (r.bs >= 0) {
                     // complete once the reach of the final best lies inside what has been scanned
                     const float need = reach_of(g, fminf(bound, r.best), r2_ub);
                     if (need <= done) mode = kDone;
-                    else if (need <= max_reach2) thr = need;
+                    else if (need <= max_reach2) thr = widen(need, slack, max_reach2);
                     else { mode = kCoop; VB_STAT(4, 1); }
                 } else if (done < max_reach2) {
                     thr = max_reach2;  // nothing within the probe: everything this path may search
@@ -697,6 +726,7 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
         if (!__any_sync(FULL, mode == kScan)) break;
     }
     if (mode == kScan) mode = kCoop;  // still open after two rounds
+    const bool lane_private = mode == kDone && valid;  // every cell with gap2 <= done was scanned by this lane
     const unsigned coop = __ballot_sync(FULL, mode == kCoop);
     VB_STAT(3, mode == kCoop);
     if (coop && (threadIdx.x & 31) == 0) VB_STAT(10, 1);
@@ -705,8 +735,20 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
         if (mode == kCoop) r = rc;
     }
     *d2_out = 0.0;
+    if (sec_out) *sec_out = -1.0f;
     if (!valid) return -1;
-    return nn_decide(G, r, c, qx, qy, qz, r2, r2_ub, d2_out);
+    bool unique = false;
+    const int bs = nn_decide(G, r, c, qx, qy, qz, r2, r2_ub, d2_out, &unique);
+    if (sec_out && unique) {
+        // scanned points other than r.bs: d32 >= r.second, hence true d2 >= r.second - band(r.second); points
+        // of cells never listed lie beyond `done` (the gap test is deflated).  After the cooperative walk only
+        // the reach of the best is known to be covered.
+        const float reach = reach_of(g, fminf(bound, r.best), r2_ub);
+        const float cover = lane_private ? fminf(done, widen(reach, slack, max_reach2)) : reach;
+        const float m = fminf(r.second, cover);
+        *sec_out = m - band(g, m);
+    }
+    return bs;
 }
 
 // ---- warp-per-query search --------------------------------------------------------------------------------

@@ -75,9 +75,23 @@ struct ProbDesc {
 };
 
 struct PassParams {
-    double r2;    // (double)(float)(max_dist^2)  (KDTreeFlann.cpp:185)
-    float r2_ub;  // f32 upper bound of r2 including the screening band
+    double r2;      // (double)(float)(max_dist^2)  (KDTreeFlann.cpp:185)
+    float r2_ub;    // f32 upper bound of r2 including the screening band
+    float slack;    // how far beyond the answer's reach a search looks, so that its result survives small moves
+    float pos_err;  // bound on the error of a distance between two centred-f32 query positions
 };
+
+#ifndef VB_SLACK_PCT
+#define VB_SLACK_PCT 8
+#endif
+inline PassParams make_pass_params(const GridParams &g, double max_dist) {
+    PassParams pp;
+    pp.r2 = (double)(float)(max_dist * max_dist);
+    pp.r2_ub = r2_upper_bound(g, pp.r2);
+    pp.slack = g.fine * (VB_SLACK_PCT * 0.01f);
+    pp.pos_err = g.band_a;  // band_a = 2 sqrt(3) e with e the per-axis error of such a difference: a 2x margin
+    return pp;
+}
 
 struct SolveParams {
     double rel_fitness, rel_rmse;
@@ -146,6 +160,7 @@ struct __align__(16) WarpScratch {
     };
 };
 constexpr int kPart = 64;  // doubles per warp partial: the 8x8 Gram matrix of the staged rows
+static_assert(32 * kPtsPerThread <= 256, "hard_ids holds a warp's point ids in one byte");
 
 // D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor cores (DMMA).  Lane l holds A[l>>2][l&3], B[l&3][l>>2] and
 // D[l>>2][2(l&3) + {0,1}].
@@ -155,116 +170,263 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
+// what a source point remembers from its last search (16 B, same indexing as corr_s): the query position then
+// (centred f32, as QueryCtx) and `sec`, a lower bound of the true squared distance from there to every target
+// point other than its match.  memset 0xff = NaN = "knows nothing".
+struct __align__(16) NNCache {
+    float qx, qy, qz, sec;
+};
+
 // One ICP correspondence pass for every active problem: transform + radius-bounded 1-NN + estimator
-// products + reduction.  grid = one block per kChunk source points of one problem.
+// products + reduction.  grid = one block per kChunk source points of one problem; every warp owns
+// kPtsPerThread batches of 32 consecutive (spatially sorted) points.
+//
+// 1. Cached-neighbour test (Greenspan & Godin 2001, exact): a point whose last search left the bound `sec`
+//    and which has since moved by delta still has the same nearest neighbour b if
+//    |q - b| < sqrt(sec) - delta (triangle inequality, all f32 error bands on the safe side).  Such a point
+//    needs no search at all: its row goes straight into the estimator sums.  Once an alignment settles this
+//    is nearly every point, and the pass becomes a streaming gather/reduce.
+// 2. The points that fail the test are compacted per warp (ballot ranks, deterministic) and searched 32 at a
+//    time with all lanes busy (nn_search_hybrid); each search refreshes the point's cache.
+// The decision is always taken in double from the exact coordinates: d2 = |q - b|^2 with FLANN's operation
+// order, accepted iff d2 < (double)(float)(r*r).
 //
 // Estimator sums: every matched lane stages one row x of 8 doubles — point-to-plane [J (6), r, 0] with
 // r = (vs - vt).nt, J = [vs x nt ; nt] (TransformationEstimation.cpp:87-89); point-to-point
 // [s' (3), d' (3), 1, 0] with (s', d') = (vs - c, vt - c) — and the warp accumulates the Gram matrix
-// sum_i x_i x_i^T with 8 DMMA instructions per 32 points: JTJ = D[0..5][0..5], JTr = D[0..5][6]
+// sum_i x_i x_i^T with 8 DMMA instructions per 32 rows: JTJ = D[0..5][0..5], JTr = D[0..5][6]
 // (resp. the umeyama moments sum d' s'^T = D[3..5][0..2], sum s' = D[0..2][6], sum d' = D[3..5][6]).  The
-// accumulator fragment lives in two registers per lane across the warp's batches.  (The first version
-// formed 27 products per lane and reduced 32 slots with a 31-step shuffle tree: ~280 instructions and 64
-// live registers per batch.)
+// accumulator fragment lives in two registers per lane for the whole warp.  (The first version formed 27
+// products per lane and reduced 32 slots with a 31-step shuffle tree: ~280 instructions and 64 live
+// registers per batch.)
 template <int MODE>
-__global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass(GridDev G, const double *__restrict__ src_xyz,
-                                                   const BlockTask *__restrict__ tasks,
-                                                   const ProbState *__restrict__ states,
-                                                   double *__restrict__ partials, int *__restrict__ corr_s,
-                                                   PassParams pp) {
-    const BlockTask task = tasks[blockIdx.x];
-    const ProbState *st = states + task.prob;
-    if (st->done) return;
-    __shared__ WarpScratch scratch[kPassWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpScratch &ws = scratch[warp];
+struct PassCtx {
+    const GridDev &G;
+    const double *T;  // the problem's current transform (global memory, warp-uniform loads)
     double c0 = 0.0, c1 = 0.0;  // this lane's two entries of the warp's Gram matrix
-    double sum_d2 = 0.0;        // exact NN distances (Registration.cpp:68), warp total in every lane
+    double sum_d2 = 0.0;        // exact NN distances (Registration.cpp:68), this lane's share
     int count = 0;
-#pragma unroll 1
-    for (int k = 0; k < kPtsPerThread; k++) {
-        // a warp owns kPtsPerThread consecutive batches of 32 consecutive (spatially sorted) points
-        const int local = (warp * kPtsPerThread + k) * 32 + lane;
-        const bool valid = local < task.count;
-        double d2 = 0.0, vs[3] = {0, 0, 0};
-        QueryCtx c;
-        bool inside = false;
-        int prior = -1;
-        if (valid) {
-            prior = corr_s[task.corr_begin + local];  // last iteration's match: a bound for this one
-#ifndef VB_NO_PRIOR_PREFETCH
-            if (prior >= 0) {
-                // most likely the match again: have its exact point / normal in L1 by the time the decision needs them
-                prefetch_l1(G.xyz + 3 * (int64_t)prior);
-                if (MODE == 1) prefetch_l1(G.nrm + 3 * (int64_t)prior);
-            }
-#endif
-            const double *p = src_xyz + 3 * (int64_t)(task.src_begin + local);
-            const double px = p[0], py = p[1], pz = p[2];
-            const double *T = st->T;  // warp-uniform broadcast loads (not held in registers across the search)
-            vs[0] = T[0] * px + T[1] * py + T[2] * pz + T[3];
-            vs[1] = T[4] * px + T[5] * py + T[6] * pz + T[7];
-            vs[2] = T[8] * px + T[9] * py + T[10] * pz + T[11];
-            inside = make_query(G.p, vs[0], vs[1], vs[2], c);
+
+    __device__ __forceinline__ PassCtx(const GridDev &g, const double *t) : G(g), T(t) {}
+
+    __device__ __forceinline__ void transform(const double *__restrict__ p, double (&vs)[3]) const {
+        const double px = p[0], py = p[1], pz = p[2];
+        vs[0] = T[0] * px + T[1] * py + T[2] * pz + T[3];
+        vs[1] = T[4] * px + T[5] * py + T[6] * pz + T[7];
+        vs[2] = T[8] * px + T[9] * py + T[10] * pz + T[11];
+    }
+
+    // the exact decision for match candidate bs (>= 0) and, if accepted, the lane's estimator row
+    __device__ __forceinline__ bool row_of(int bs, const double (&vs)[3], double r2, double (&x)[8]) {
+        const double *t = G.xyz + 3 * (int64_t)bs;
+        const double vt[3] = {t[0], t[1], t[2]};
+        const double d2 = l2_exact(vs[0], vs[1], vs[2], vt);
+        if (!(d2 < r2)) return false;
+        if (MODE == 1) {
+            const double *nn = G.nrm + 3 * (int64_t)bs;
+            const double nt[3] = {nn[0], nn[1], nn[2]};
+            x[0] = vs[1] * nt[2] - vs[2] * nt[1];
+            x[1] = vs[2] * nt[0] - vs[0] * nt[2];
+            x[2] = vs[0] * nt[1] - vs[1] * nt[0];
+            x[3] = nt[0]; x[4] = nt[1]; x[5] = nt[2];
+            x[6] = (vs[0] - vt[0]) * nt[0] + (vs[1] - vt[1]) * nt[1] + (vs[2] - vt[2]) * nt[2];
+        } else {
+            // cref = translation part of T: keeps the moments O(object size) instead of O(scene size)
+            const double cr[3] = {T[3], T[7], T[11]};
+            x[0] = vs[0] - cr[0]; x[1] = vs[1] - cr[1]; x[2] = vs[2] - cr[2];
+            x[3] = vt[0] - cr[0]; x[4] = vt[1] - cr[1]; x[5] = vt[2] - cr[2];
+            x[6] = 1.0;
         }
-        // every lane takes part in the search, lanes without a query just ride along
-#ifdef VB_SEARCH_COOP_ONLY
-        (void)prior;
-        const int bs = nn_search_warp(G, inside, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, &d2);
-#else
-        const int bs = nn_search_hybrid<32>(G, inside, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, prior, ws.runs, &d2);
-#endif
-        const bool matched = bs >= 0;
-        double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (valid) {
-            if (matched) {
-                const double *t = G.xyz + 3 * (int64_t)bs;
-                const double vt[3] = {t[0], t[1], t[2]};
-                if (MODE == 1) {
-                    const double *nn = G.nrm + 3 * (int64_t)bs;
-                    const double nt[3] = {nn[0], nn[1], nn[2]};
-                    x[0] = vs[1] * nt[2] - vs[2] * nt[1];
-                    x[1] = vs[2] * nt[0] - vs[0] * nt[2];
-                    x[2] = vs[0] * nt[1] - vs[1] * nt[0];
-                    x[3] = nt[0]; x[4] = nt[1]; x[5] = nt[2];
-                    x[6] = (vs[0] - vt[0]) * nt[0] + (vs[1] - vt[1]) * nt[1] + (vs[2] - vt[2]) * nt[2];
-                } else {
-                    // cref = translation part of T: keeps the moments O(object size) instead of O(scene size)
-                    const double cr[3] = {st->T[3], st->T[7], st->T[11]};
-                    x[0] = vs[0] - cr[0]; x[1] = vs[1] - cr[1]; x[2] = vs[2] - cr[2];
-                    x[3] = vt[0] - cr[0]; x[4] = vt[1] - cr[1]; x[5] = vt[2] - cr[2];
-                    x[6] = 1.0;
-                }
-            }
-            corr_s[task.corr_begin + local] = bs;  // sorted position; vb200_batch_corr maps it to the caller's index
-        }
+        sum_d2 += d2;
+        count += 1;
+        return true;
+    }
+
+    // all 32 lanes: stage the rows (zeros for lanes without a match) and accumulate their Gram matrix
+    __device__ __forceinline__ void accumulate(double *rows, const double (&x)[8]) {
+        const int lane = threadIdx.x & 31;
         __syncwarp();  // the run lists are dead: the scratch now holds the estimator rows
-        {
-            double2 *row = reinterpret_cast<double2 *>(ws.rows + lane * kRowStride);
-            row[0] = make_double2(x[0], x[1]);
-            row[1] = make_double2(x[2], x[3]);
-            row[2] = make_double2(x[4], x[5]);
-            row[3] = make_double2(x[6], x[7]);
-        }
+        double2 *row = reinterpret_cast<double2 *>(rows + lane * kRowStride);
+        row[0] = make_double2(x[0], x[1]);
+        row[1] = make_double2(x[2], x[3]);
+        row[2] = make_double2(x[4], x[5]);
+        row[3] = make_double2(x[6], x[7]);
         __syncwarp();
 #pragma unroll
         for (int ch = 0; ch < 8; ch++) {
-            const double a = ws.rows[(4 * ch + (lane & 3)) * kRowStride + (lane >> 2)];
+            const double a = rows[(4 * ch + (lane & 3)) * kRowStride + (lane >> 2)];
             dmma_m8n8k4(c0, c1, a, a);
         }
-        // sum of exact NN distances and the inlier count (fixed-order butterfly: deterministic)
-        double dd = matched ? d2 : 0.0;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
-        sum_d2 += dd;
-        count += __popc(__ballot_sync(0xffffffffu, matched));
-        __syncwarp();  // rows consumed before the next batch lists its runs
+        __syncwarp();  // rows consumed before anything else reuses the scratch
     }
-    // D[l>>2][2(l&3) + {0,1}] = entries 2l, 2l+1 of the row-major 8x8: one coalesced 512-byte row per warp.
-    // Row 7 of D is identically zero (x[7] = 0); its last two entries carry the count and sum d2.
-    if (lane == 31) { c0 = (double)count; c1 = sum_d2; }
-    double2 *out = reinterpret_cast<double2 *>(partials + ((int64_t)blockIdx.x * kPassWarps + warp) * kPart);
-    out[lane] = make_double2(c0, c1);
+
+    // the warp's partial: D[l>>2][2(l&3) + {0,1}] = entries 2l, 2l+1 of the row-major 8x8, one coalesced
+    // 512-byte row.  Row 7 of D is identically zero (x[7] = 0); its last two entries carry the inlier count
+    // and the sum of exact NN distances (fixed-order butterfly: deterministic).
+    __device__ __forceinline__ void write_partial(double *__restrict__ out_row) {
+        const int lane = threadIdx.x & 31;
+        double dd = sum_d2;
+        int cnt = count;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            dd += __shfl_xor_sync(0xffffffffu, dd, o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        double a = c0, b = c1;
+        if (lane == 31) { a = (double)cnt; b = dd; }
+        reinterpret_cast<double2 *>(out_row)[lane] = make_double2(a, b);
+    }
+};
+
+#ifndef VB_COOP_WARP_LANES
+#define VB_COOP_WARP_LANES 12  // more lanes than this with a long reach: the whole warp takes the shared walk
+#endif
+#ifndef VB_PASS_A_MINBLOCKS
+#define VB_PASS_A_MINBLOCKS 12
+#endif
+constexpr int kRowsPerBlock = 2 * kPassWarps;  // partial rows per block: k_pass_a's warps, then k_pass_b's
+
+// ---- pass, part A: every point.  Streaming: transform, cached-neighbour test, and for the points it settles
+// the exact decision and the estimator row.  The rest are listed per warp (ballot ranks: deterministic order)
+// for part B.  No search code in here, so the kernel runs at high occupancy: it is a gather/reduce bound by
+// memory latency and bandwidth.
+template <int MODE>
+__global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
+    GridDev G, const double *__restrict__ src_xyz, const BlockTask *__restrict__ tasks,
+    const ProbState *__restrict__ states, double *__restrict__ partials, int *__restrict__ corr_s,
+    const NNCache *__restrict__ cache, unsigned char *__restrict__ hard_ids, int *__restrict__ hard_cnt,
+    PassParams pp) {
+    const BlockTask task = tasks[blockIdx.x];
+    const ProbState *st = states + task.prob;
+    if (st->done) return;
+    __shared__ __align__(16) double rows_sh[kPassWarps][32 * kRowStride];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PassCtx<MODE> ctx(G, st->T);
+    unsigned char *my_hard = hard_ids + ((int64_t)blockIdx.x * kPassWarps + warp) * (32 * kPtsPerThread);
+    int nhard = 0;  // warp-uniform
+#pragma unroll 1
+    for (int k = 0; k < kPtsPerThread; k++) {
+        const int local = (warp * kPtsPerThread + k) * 32 + lane;
+        const bool valid = local < task.count;
+        double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        bool hard = false;
+        if (valid) {
+            double vs[3];
+            ctx.transform(src_xyz + 3 * (int64_t)(task.src_begin + local), vs);
+            QueryCtx c;
+            const bool inside = make_query(G.p, vs[0], vs[1], vs[2], c);
+            const int slot = task.corr_begin + local;
+            if (!inside) {
+                corr_s[slot] = -1;  // farther than a cell outside the grid: no neighbour within the radius
+            } else {
+                hard = true;
+#ifndef VB_NO_NN_CACHE
+                const int prior = corr_s[slot];
+                if (prior >= 0) {
+                    const NNCache m = cache[slot];
+                    const float4 t = __ldg(G.hi + prior);
+                    const float dx = c.qx - t.x, dy = c.qy - t.y, dz = c.qz - t.z;
+                    const float d1 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    const float mx = c.qx - m.qx, my = c.qy - m.qy, mz = c.qz - m.qz;
+                    const float moved = sqrtf(fmaf(mz, mz, fmaf(my, my, mx * mx)));
+                    // |q - b| (upper bound) + move (upper bound) < distance to anything else then (lower bound);
+                    // NaN (no cache) compares false
+                    const float lhs = sqrtf(d1 + band(G.p, d1)) * 1.000001f + moved * 1.000001f + pp.pos_err;
+                    if (lhs < sqrtf(m.sec) * 0.999999f) {
+                        hard = false;
+                        // still the nearest, but it may have left the radius: then there is no correspondence
+                        // (and nothing to remember: corr_s doubles as the correspondence list)
+                        if (!ctx.row_of(prior, vs, pp.r2, x)) corr_s[slot] = -1;
+                    }
+                }
+#endif
+            }
+        }
+#ifdef VB_STATS
+        if (valid) {
+            const int pr = corr_s[task.corr_begin + local];
+            VB_STAT(12, hard);
+            VB_STAT(13, hard && pr < 0);
+            VB_STAT(14, hard && pr >= 0 && !(cache[task.corr_begin + local].sec >= 0.0f));
+        }
+#endif
+        const unsigned hm = __ballot_sync(0xffffffffu, hard);
+        if (hard) my_hard[nhard + __popc(hm & ((1u << lane) - 1u))] = (unsigned char)(k * 32 + lane);
+        nhard += __popc(hm);
+        if (hm != 0xffffffffu) ctx.accumulate(rows_sh[warp], x);  // warp-uniform; nothing to add when every lane is hard
+    }
+    if (lane == 0) hard_cnt[blockIdx.x * kPassWarps + warp] = nhard;
+    ctx.write_partial(partials + ((int64_t)blockIdx.x * kRowsPerBlock + warp) * kPart);
+}
+
+// ---- pass, part B: the listed points of a part-A block, 32 searches at a time with every lane busy.  Each
+// search refreshes the point's cache entry.  One WARP per CUDA block (grid = 4 x part A's): once an alignment
+// settles most lists hold a handful of points, and single-warp blocks let an SM keep ~24 of those short,
+// latency-bound batches in flight instead of 6 four-warp blocks with one live warp each.
+template <int MODE>
+__global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b(
+    GridDev G, const double *__restrict__ src_xyz, const BlockTask *__restrict__ tasks,
+    const ProbState *__restrict__ states, double *__restrict__ partials, int *__restrict__ corr_s,
+    NNCache *__restrict__ cache, const unsigned char *__restrict__ hard_ids, const int *__restrict__ hard_cnt,
+    PassParams pp) {
+    const int blk = blockIdx.x / kPassWarps, warp = blockIdx.x % kPassWarps, lane = threadIdx.x;
+    const BlockTask task = tasks[blk];
+    const ProbState *st = states + task.prob;
+    if (st->done) return;
+    // the block's list = its warps' lists of part A, concatenated
+    int seg_end[kPassWarps];
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < kPassWarps; w++) {
+        total += hard_cnt[blk * kPassWarps + w];
+        seg_end[w] = total;
+    }
+    __shared__ WarpScratch ws;
+    PassCtx<MODE> ctx(G, st->T);
+#pragma unroll 1
+    for (int h0 = 32 * warp; h0 < total; h0 += 32 * kPassWarps) {
+        const bool live = h0 + lane < total;
+        double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double vs[3] = {0, 0, 0}, d2 = 0.0;
+        QueryCtx c;
+        int prior = -1, slot = 0;
+        float slack = 0.0f;
+        if (live) {
+            const int h = h0 + lane;
+            int w = 0, base = 0;
+#pragma unroll
+            for (int i = 0; i < kPassWarps - 1; i++)
+                if (h >= seg_end[i]) { w = i + 1; base = seg_end[i]; }
+            const int id = hard_ids[((int64_t)blk * kPassWarps + w) * (32 * kPtsPerThread) + (h - base)];
+            const int local = (w * kPtsPerThread + (id >> 5)) * 32 + (id & 31);
+            slot = task.corr_begin + local;
+            ctx.transform(src_xyz + 3 * (int64_t)(task.src_begin + local), vs);
+            make_query(G.p, vs[0], vs[1], vs[2], c);  // inside the grid, or it would not be listed
+            prior = corr_s[slot];  // last iteration's match: a bound for this search
+            // looking further than the answer needs only pays when the point is about to settle: one that
+            // has just moved by more than the slack will fail the next test anyway
+            const NNCache m = cache[slot];
+            const float mx = c.qx - m.qx, my = c.qy - m.qy, mz = c.qz - m.qz;
+            if (fmaf(mz, mz, fmaf(my, my, mx * mx)) < 4.0f * pp.slack * pp.slack) slack = pp.slack;  // NaN: no
+        }
+        float sec = -1.0f;
+#ifdef VB_SEARCH_COOP_ONLY
+        const int bs = nn_search_warp(G, live, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, &d2);
+#else
+        const int bs = nn_search_hybrid<32>(G, live, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, prior, ws.runs, &d2,
+                                            slack, &sec, VB_COOP_WARP_LANES);
+#endif
+        if (live) {
+            corr_s[slot] = bs;  // sorted position; vb200_batch_corr maps it to the caller's index
+            NNCache m;
+            m.qx = c.qx; m.qy = c.qy; m.qz = c.qz;
+            m.sec = bs >= 0 ? sec : -1.0f;
+            cache[slot] = m;
+            if (bs >= 0) ctx.row_of(bs, vs, pp.r2, x);
+        }
+        ctx.accumulate(ws.rows, x);
+    }
+    ctx.write_partial(partials + ((int64_t)blk * kRowsPerBlock + kPassWarps + warp) * kPart);
 }
 
 // ---- estimator solves from the reduced slots ---------------------------------------------------------
@@ -322,8 +484,8 @@ __device__ __forceinline__ void reduce_partials(const ProbDesc &pd, const double
                                                 double (*sw)[kPart], double *tot) {
     const int e = threadIdx.x & (kPart - 1), grp = threadIdx.x / kPart;  // 4 groups of 64 threads
     double s = 0.0;
-    for (int b = grp; b < pd.blk_count * kPassWarps; b += 4)
-        s += partials[((int64_t)pd.blk_begin * kPassWarps + b) * kPart + e];
+    for (int b = grp; b < pd.blk_count * kRowsPerBlock; b += 4)
+        s += partials[((int64_t)pd.blk_begin * kRowsPerBlock + b) * kPart + e];
     sw[grp][e] = s;
     __syncthreads();
     if (threadIdx.x < kPart) sw[0][e] = ((sw[0][e] + sw[1][e]) + sw[2][e]) + sw[3][e];
@@ -589,6 +751,9 @@ struct Batch {
     BlockTask *d_tasks = nullptr;
     double *d_partials = nullptr;
     int *d_corr = nullptr;
+    NNCache *d_cache = nullptr;              // per (problem, point): what its last search proved (k_pass_a/b)
+    unsigned char *d_hard_ids = nullptr;     // per block and warp: the points part A left for part B
+    int *d_hard_cnt = nullptr;
     int64_t launches = 0;
     int iter_base = 0;                       // running pass index for vb200_batch_iterate
     double *d_totals = nullptr;              // P x kAcc, library-owned unless the caller supplied a buffer
@@ -600,8 +765,10 @@ struct Batch {
 
 static void batch_free_problems(Batch *b) {
     cudaStream_t st = b->scene->stream;
-    void *ptrs[7] = {b->d_probs, b->d_states, b->d_tasks, b->d_partials, b->d_corr, b->d_totals, b->d_npts_global};
-    b->d_totals = nullptr; b->d_npts_global = nullptr;
+    void *ptrs[10] = {b->d_probs, b->d_states, b->d_tasks, b->d_partials, b->d_corr, b->d_totals, b->d_npts_global,
+                      b->d_cache, b->d_hard_ids, b->d_hard_cnt};
+    b->d_totals = nullptr; b->d_npts_global = nullptr; b->d_cache = nullptr;
+    b->d_hard_ids = nullptr; b->d_hard_cnt = nullptr;
     for (void *q : ptrs)
         if (q) cudaFreeAsync(q, st);
     b->d_probs = nullptr; b->d_states = nullptr; b->d_tasks = nullptr; b->d_partials = nullptr; b->d_corr = nullptr;
@@ -701,7 +868,7 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
     VB_CUDA(cudaMallocAsync((void **)&b->d_probs, sizeof(ProbDesc) * (size_t)std::max(P, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_states, sizeof(ProbState) * (size_t)std::max(P, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_tasks, sizeof(BlockTask) * (size_t)std::max(b->nblk, 1), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_partials, sizeof(double) * kPart * kPassWarps * (size_t)std::max(b->nblk, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_partials, sizeof(double) * kPart * kRowsPerBlock * (size_t)std::max(b->nblk, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_corr, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
     if (P) {
         VB_CUDA(cudaMemcpyAsync(b->d_probs, b->probs.data(), sizeof(ProbDesc) * (size_t)P, cudaMemcpyHostToDevice, st));
@@ -710,10 +877,32 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
     if (b->nblk)
         VB_CUDA(cudaMemcpyAsync(b->d_tasks, tasks.data(), sizeof(BlockTask) * (size_t)b->nblk, cudaMemcpyHostToDevice, st));
     VB_CUDA(cudaMemsetAsync(b->d_corr, 0xff, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_cache, sizeof(NNCache) * (size_t)std::max<int64_t>(corr, 1), st));
+    VB_CUDA(cudaMemsetAsync(b->d_cache, 0xff, sizeof(NNCache) * (size_t)std::max<int64_t>(corr, 1), st));  // NaN
+    VB_CUDA(cudaMallocAsync((void **)&b->d_hard_ids, (size_t)kChunk * (size_t)std::max(b->nblk, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_hard_cnt, sizeof(int) * kPassWarps * (size_t)std::max(b->nblk, 1), st));
     VB_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
     return VB200_OK;
 }
 
+
+// one correspondence pass = part A (every point, streaming) + part B (the points that need a search)
+static void launch_pass(Batch *b, bool plane, const PassParams &pp) {
+    Scene *sc = b->scene;
+    cudaStream_t st = sc->stream;
+    if (plane) {
+        k_pass_a<1><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
+                                                  b->d_cache, b->d_hard_ids, b->d_hard_cnt, pp);
+        k_pass_b<1><<<b->nblk * kPassWarps, 32, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
+                                                  b->d_cache, b->d_hard_ids, b->d_hard_cnt, pp);
+    } else {
+        k_pass_a<0><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
+                                                  b->d_cache, b->d_hard_ids, b->d_hard_cnt, pp);
+        k_pass_b<0><<<b->nblk * kPassWarps, 32, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
+                                                  b->d_cache, b->d_hard_ids, b->d_hard_cnt, pp);
+    }
+    b->launches += 2;
+}
 
 static int batch_run(Batch *b, int estimator, const double *gravity, double max_dist, double rel_fitness,
                      double rel_rmse, int max_iter) {
@@ -725,9 +914,7 @@ static int batch_run(Batch *b, int estimator, const double *gravity, double max_
     const bool plane = estimator != VB200_EST_P2P;
     if (plane && (!b->has_normals || !sc->has_normals)) return VB200_ERR_NORMALS;
     if (b->P == 0) return VB200_OK;
-    PassParams pp;
-    pp.r2 = (double)(float)(max_dist * max_dist);
-    pp.r2_ub = r2_upper_bound(sc->grid.p, pp.r2);
+    const PassParams pp = make_pass_params(sc->grid.p, max_dist);
     SolveParams sp;
     sp.rel_fitness = rel_fitness;
     sp.rel_rmse = rel_rmse;
@@ -741,11 +928,7 @@ static int batch_run(Batch *b, int estimator, const double *gravity, double max_
     }
     for (int it = 0; it <= max_iter; it++) {
         if (b->nblk) {
-            if (plane)
-                k_pass<1><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
-            else
-                k_pass<0><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
-            b->launches++;
+            launch_pass(b, plane, pp);
         }
         k_solve<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, sp, it);
         b->launches++;
@@ -761,8 +944,7 @@ static int make_params(Batch *b, int estimator, const double *gravity, double ma
     if (!(max_dist > 0.0)) return VB200_ERR_DISTANCE;
     if (max_dist > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
     if (estimator != VB200_EST_P2P && (!b->has_normals || !sc->has_normals)) return VB200_ERR_NORMALS;
-    pp->r2 = (double)(float)(max_dist * max_dist);
-    pp->r2_ub = r2_upper_bound(sc->grid.p, pp->r2);
+    *pp = make_pass_params(sc->grid.p, max_dist);
     sp->estimator = estimator;
     sp->g[0] = 0.0; sp->g[1] = 1.0; sp->g[2] = 0.0;
     if (estimator == VB200_EST_P2PLANE_GRAVITY && gravity) {
@@ -787,11 +969,7 @@ static int batch_pass(Batch *b, int estimator, double max_dist) {
     }
     double *totals = b->d_totals_ext ? b->d_totals_ext : b->d_totals;
     if (b->nblk) {
-        if (estimator != VB200_EST_P2P)
-            k_pass<1><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
-        else
-            k_pass<0><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
-        b->launches++;
+        launch_pass(b, estimator != VB200_EST_P2P, pp);
     }
     k_reduce<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, estimator != VB200_EST_P2P, totals);
     b->launches++;
@@ -834,9 +1012,7 @@ static int batch_iterate(Batch *b, int estimator, const double *gravity, double 
     const bool plane = estimator != VB200_EST_P2P;
     if (plane && (!b->has_normals || !sc->has_normals)) return VB200_ERR_NORMALS;
     if (b->P == 0 || b->nblk == 0) return VB200_OK;
-    PassParams pp;
-    pp.r2 = (double)(float)(max_dist * max_dist);
-    pp.r2_ub = r2_upper_bound(sc->grid.p, pp.r2);
+    const PassParams pp = make_pass_params(sc->grid.p, max_dist);
     SolveParams sp;
     sp.rel_fitness = sp.rel_rmse = -1.0;  // |delta| < -1 never holds: no convergence exit
     sp.max_iter = 0x7fffffff;
@@ -852,14 +1028,11 @@ static int batch_iterate(Batch *b, int estimator, const double *gravity, double 
     const bool timed = n_iter == 1;  // per-kernel events only make sense around a single iteration
     for (int it = 0; it < n_iter; it++) {
         if (timed) VB_CUDA(cudaEventRecord(b->ev[0], st));
-        if (plane)
-            k_pass<1><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
-        else
-            k_pass<0><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr, pp);
+        launch_pass(b, plane, pp);
         if (timed) VB_CUDA(cudaEventRecord(b->ev[1], st));
         k_solve<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, sp, b->iter_base++);
         if (timed) VB_CUDA(cudaEventRecord(b->ev[2], st));
-        b->launches += 2;
+        b->launches += 1;
     }
     b->ev_valid = timed;
     VB_CUDA(cudaGetLastError());
