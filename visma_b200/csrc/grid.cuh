@@ -581,6 +581,44 @@ __device__ __forceinline__ int scan_runs(const GridDev &G, const QueryCtx &c, in
     return steps;
 }
 
+// The three smallest f32 distances among a lane's listed runs and the positions of the first two: a second
+// look at the same candidates, taken only by the rare lanes whose winner and runner-up are too close for a
+// single cached neighbour (see nn_search_hybrid).  Runs beyond `cut` are skipped, as the first scan did.
+struct Top3 {
+    float d0, d1, d2;
+    int s0, s1;
+};
+
+template <int TPB>
+__device__ __forceinline__ Top3 top3_of_runs(const GridDev &G, const QueryCtx &c, int nruns, float cut,
+                                             const LaneRuns<TPB> &L) {
+    const int tid = threadIdx.x & (TPB - 1);
+    Top3 t;
+    t.d0 = t.d1 = t.d2 = 3.0e38f;
+    t.s0 = t.s1 = -1;
+    for (int ri = 0; ri < nruns; ++ri) {
+        const unsigned w = L.w[ri][tid];
+        if (__uint_as_float(w & ~kRunLenMask) > cut) continue;
+        int s = L.s0[ri][tid];
+        const int e = s + (int)(w & kRunLenMask);
+        for (; s < e; ++s) {
+            const float4 p = __ldg(G.hi + s);
+            const float dx = c.qx - p.x, dy = c.qy - p.y, dz = c.qz - p.z;
+            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (d < t.d0) {
+                t.d2 = t.d1; t.d1 = t.d0; t.s1 = t.s0;
+                t.d0 = d; t.s0 = s;
+            } else if (d < t.d1) {
+                t.d2 = t.d1;
+                t.d1 = d; t.s1 = s;
+            } else if (d < t.d2) {
+                t.d2 = d;
+            }
+        }
+    }
+    return t;
+}
+
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // list the occupied fine cells with done < gap2 <= thr (squared distance to the query) as runs, in ONE flat
@@ -647,15 +685,17 @@ __device__ __forceinline__ int list_runs(const GridDev &G, const QueryCtx &c, fl
 // be close to the query (or -1): only ever used as an upper bound, never as an answer.
 //
 // `slack` (metric, >= 0) widens every lane-private search beyond what the answer needs, and *sec_out (nullable)
-// receives a lower bound of the TRUE squared distance from the query to every target point other than the
-// returned one (or a negative value when no such statement can be made): the caller keeps it with the query
-// position and can later prove, by the triangle inequality, that the answer is unchanged after a small move
-// (k_pass: Greenspan & Godin's cached-neighbour test for ICP).
+// receives what the search proved about everything else: sec > 0 = a lower bound of the TRUE squared distance
+// from the query to every target point other than the returned one; sec < 0 with *second_out >= 0 = the same
+// bound (-sec) for every point other than the returned one AND the runner-up *second_out; sec == -1 with no
+// runner-up = nothing.  The caller keeps it with the query position and can later prove, by the triangle
+// inequality, that the answer is unchanged after a small move (k_pass: Greenspan & Godin's cached-neighbour
+// test for ICP).
 template <int TPB>
 __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, const QueryCtx &c, double qx, double qy,
                                                 double qz, double r2, float r2_ub, int prior, LaneRuns<TPB> &L,
                                                 double *d2_out, float slack = 0.0f, float *sec_out = nullptr,
-                                                int coop_lanes = 32) {
+                                                int coop_lanes = 32, int *second_out = nullptr) {
     const unsigned FULL = 0xffffffffu;
     static_assert((TPB & (TPB - 1)) == 0, "TPB must be a power of two");
     const GridParams &g = G.p;
@@ -688,6 +728,7 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
     VB_STAT(1, bound < r2_ub);
     if ((threadIdx.x & 31) == 0) VB_STAT(11, 1);
     float done = -1.0f;  // every cell with gap2 <= done has been scanned
+    int nscans = 0, last_nruns = 0;  // rounds this lane scanned, and the length of its latest list
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
         int nruns = 0, steps = 0;
@@ -700,6 +741,8 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
                 VB_STAT(7, nruns);
                 steps = scan_runs<TPB>(G, c, nruns, bound, r2_ub, slack, max_reach2, L, r);
                 done = thr;
+                ++nscans;
+                last_nruns = nruns;
                 if (r.bs >= 0) {
                     // complete once the reach of the final best lies inside what has been scanned
                     const float need = reach_of(g, fminf(bound, r.best), r2_ub);
@@ -736,19 +779,53 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
     }
     *d2_out = 0.0;
     if (sec_out) *sec_out = -1.0f;
-    if (!valid) return -1;
-    bool unique = false;
-    const int bs = nn_decide(G, r, c, qx, qy, qz, r2, r2_ub, d2_out, &unique);
-    if (sec_out && unique) {
-        // scanned points other than r.bs: d32 >= r.second, hence true d2 >= r.second - band(r.second); points
-        // of cells never listed lie beyond `done` (the gap test is deflated).  After the cooperative walk only
-        // the reach of the best is known to be covered.
-        const float reach = reach_of(g, fminf(bound, r.best), r2_ub);
-        const float cover = lane_private ? fminf(done, widen(reach, slack, max_reach2)) : reach;
-        const float m = fminf(r.second, cover);
-        *sec_out = m - band(g, m);
+    if (second_out) *second_out = -1;
+    if (!valid || r.bs < 0) return -1;
+    // ---- the decision, in double
+    const float bb = band(g, r.best);
+    const bool unique = r.second - r.best > bb + band(g, r.second);  // r.bs is the true nearest
+    // what this lane is known to have scanned: every cell within `cover`.  Points of cells never listed lie
+    // beyond `done` (the gap test is deflated); after the cooperative walk only the reach of the best is known.
+    const float reach = reach_of(g, fminf(bound, r.best), r2_ub);
+    const float wide = widen(reach, slack, max_reach2);
+    const float cover = lane_private ? fminf(done, wide) : reach;
+    // scanned points other than r.bs: d32 >= r.second, hence true d2 >= r.second - band(r.second)
+    const float m1 = fminf(r.second, cover);
+    const float sec1 = m1 - band(g, m1);
+    if (sec_out && lane_private && nscans == 1) {
+        // Would the answer hold as ONE cached neighbour (k_pass_a's test, before any move)?  If the runner-up is
+        // that close — or the f32 distances cannot even tell the two apart — keep BOTH: a second look at this
+        // lane's candidates finds the runner-up's position and the third-smallest distance, the winner between
+        // the two is taken in double, and the caller caches the pair with a bound on everything else.
+        // (only when the runner-up itself is what limits the bound: a lane whose bound is its scan radius —
+        // every search of an alignment's first iterations — gains nothing from a second candidate)
+        const bool lone = unique && sqrtf(r.best + bb) * 1.000001f + g.band_a < sqrtf(fmaxf(sec1, 0.0f)) * 0.999999f;
+        if (!lone && r.second < cover) {
+            const Top3 t = top3_of_runs<TPB>(G, c, last_nruns, wide, L);
+            const float m3 = fminf(t.d2, cover);
+            const float sec3 = m3 - band(g, m3);  // true d2 of every point other than the two is above this
+            if (t.s1 >= 0 && sec3 > t.d0 + band(g, t.d0)) {
+                const double da = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)t.s0);
+                const double db = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)t.s1);
+                // exact ties break to the lowest ORIGINAL index (the documented rule, as nn_exact_rescan)
+                const bool first = da < db || (da == db && __ldg(G.orig + t.s0) < __ldg(G.orig + t.s1));
+                const double dw = first ? da : db;
+                if (!(dw < r2)) return -1;
+                *d2_out = dw;
+                *sec_out = -sec3;  // negative: a two-candidate entry
+                if (second_out) *second_out = first ? t.s1 : t.s0;
+                return first ? t.s0 : t.s1;
+            }
+        }
     }
-    return bs;
+    if (unique) {
+        const double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)r.bs);
+        if (!(d < r2)) return -1;
+        *d2_out = d;
+        if (sec_out) *sec_out = sec1;
+        return r.bs;
+    }
+    return nn_exact_rescan(G, c, qx, qy, qz, r2, fminf(r.best + 2.0f * bb, r2_ub), d2_out);
 }
 
 // ---- warp-per-query search --------------------------------------------------------------------------------

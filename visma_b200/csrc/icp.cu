@@ -263,7 +263,7 @@ struct PassCtx {
     // the warp's partial: D[l>>2][2(l&3) + {0,1}] = entries 2l, 2l+1 of the row-major 8x8, one coalesced
     // 512-byte row.  Row 7 of D is identically zero (x[7] = 0); its last two entries carry the inlier count
     // and the sum of exact NN distances (fixed-order butterfly: deterministic).
-    __device__ __forceinline__ void write_partial(double *__restrict__ out_row) {
+    __device__ __forceinline__ double2 lane_pair() {
         const int lane = threadIdx.x & 31;
         double dd = sum_d2;
         int cnt = count;
@@ -274,7 +274,10 @@ struct PassCtx {
         }
         double a = c0, b = c1;
         if (lane == 31) { a = (double)cnt; b = dd; }
-        reinterpret_cast<double2 *>(out_row)[lane] = make_double2(a, b);
+        return make_double2(a, b);
+    }
+    __device__ __forceinline__ void write_partial(double *__restrict__ out_row) {
+        reinterpret_cast<double2 *>(out_row)[threadIdx.x & 31] = lane_pair();
     }
 };
 
@@ -284,7 +287,7 @@ struct PassCtx {
 #ifndef VB_PASS_A_MINBLOCKS
 #define VB_PASS_A_MINBLOCKS 12
 #endif
-constexpr int kRowsPerBlock = 2 * kPassWarps;  // partial rows per block: k_pass_a's warps, then k_pass_b's
+constexpr int kRowsPerBlock = 1 + kPassWarps;  // partial rows per block: k_pass_a's (block total), then k_pass_b's warps
 
 // ---- pass, part A: every point.  Streaming: transform, cached-neighbour test, and for the points it settles
 // the exact decision and the estimator row.  The rest are listed per warp (ballot ranks: deterministic order)
@@ -294,8 +297,8 @@ template <int MODE>
 __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
     GridDev G, const double *__restrict__ src_xyz, const BlockTask *__restrict__ tasks,
     const ProbState *__restrict__ states, double *__restrict__ partials, int *__restrict__ corr_s,
-    const NNCache *__restrict__ cache, unsigned char *__restrict__ hard_ids, int *__restrict__ hard_cnt,
-    PassParams pp) {
+    const NNCache *__restrict__ cache, int *__restrict__ second_s, unsigned char *__restrict__ hard_ids,
+    int *__restrict__ hard_cnt, PassParams pp) {
     const BlockTask task = tasks[blockIdx.x];
     const ProbState *st = states + task.prob;
     if (st->done) return;
@@ -337,6 +340,24 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
                         // still the nearest, but it may have left the radius: then there is no correspondence
                         // (and nothing to remember: corr_s doubles as the correspondence list)
                         if (!ctx.row_of(prior, vs, pp.r2, x)) corr_s[slot] = -1;
+                    } else if (m.sec < 0.0f) {
+                        // a two-candidate entry (winner and runner-up too close to tell apart for long): if both
+                        // are still nearer than anything else can be, the winner between them is taken in double
+                        const int other = second_s[slot];
+                        if (other >= 0) {
+                            const float4 u = __ldg(G.hi + other);
+                            const float ex = c.qx - u.x, ey = c.qy - u.y, ez = c.qz - u.z;
+                            const float dm = fmaxf(d1, fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+                            const float lhs2 = sqrtf(dm + band(G.p, dm)) * 1.000001f + moved * 1.000001f + pp.pos_err;
+                            if (lhs2 < sqrtf(-m.sec) * 0.999999f) {
+                                hard = false;
+                                const double da = l2_exact(vs[0], vs[1], vs[2], G.xyz + 3 * (int64_t)prior);
+                                const double db = l2_exact(vs[0], vs[1], vs[2], G.xyz + 3 * (int64_t)other);
+                                const bool first = da < db || (da == db && __ldg(G.orig + prior) < __ldg(G.orig + other));
+                                if (!first) { corr_s[slot] = other; second_s[slot] = prior; }
+                                if (!ctx.row_of(first ? prior : other, vs, pp.r2, x)) corr_s[slot] = -1;
+                            }
+                        }
                     }
                 }
 #endif
@@ -356,7 +377,73 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
         if (hm != 0xffffffffu) ctx.accumulate(rows_sh[warp], x);  // warp-uniform; nothing to add when every lane is hard
     }
     if (lane == 0) hard_cnt[blockIdx.x * kPassWarps + warp] = nhard;
-    ctx.write_partial(partials + ((int64_t)blockIdx.x * kRowsPerBlock + warp) * kPart);
+    // one partial row per block: the warps' Gram matrices summed in warp order (rows_sh is free again)
+    const double2 mine = ctx.lane_pair();
+    __syncthreads();
+    double2 *red = reinterpret_cast<double2 *>(&rows_sh[0][0]);
+    red[warp * 32 + lane] = mine;
+    __syncthreads();
+    if (warp == 0) {
+        double2 t = red[lane];
+#pragma unroll
+        for (int w = 1; w < kPassWarps; w++) { t.x += red[w * 32 + lane].x; t.y += red[w * 32 + lane].y; }
+        reinterpret_cast<double2 *>(partials + (int64_t)blockIdx.x * kRowsPerBlock * kPart)[lane] = t;
+    }
+}
+
+// entry t of the 32 estimator slots from a summed 8x8 Gram matrix D.  Slot layout: point-to-plane 0..20 JTJ
+// upper triangle row-major, 21..26 JTr; point-to-point 0..2 sum s', 3..5 sum d', 6..14 sum d' s'^T,
+// 15 sum |s'|^2; both 30 = sum d2, 31 = count.
+__device__ __forceinline__ double slot_from_gram(const double *D, bool plane, int t) {
+    double v = 0.0;
+    if (t == kSlotD2) v = D[63];
+    else if (t == kSlotCount) v = D[62];
+    else if (plane) {
+        if (t < 21) {
+            int a = 0, rem = t;
+            while (rem >= 6 - a) { rem -= 6 - a; ++a; }  // slot t = (a, b) of the upper triangle, b >= a
+            v = D[8 * a + a + rem];
+        } else if (t < 27) {
+            v = D[8 * (t - 21) + 6];
+        }
+    } else {
+        if (t < 6) v = D[8 * t + 6];
+        else if (t < 15) v = D[8 * (3 + (t - 6) / 3) + (t - 6) % 3];
+        else if (t == 15) v = (D[0] + D[9]) + D[18];
+    }
+    return v;
+}
+
+__device__ void solve_from_totals(const double *tot, double npts, ProbState *st, const SolveParams &sp, int pass_index);
+
+// The iteration tail run by the last part-B warp of a problem (kept out of line: it is rare and register-hungry).
+static __device__ __noinline__ void iteration_tail(const ProbDesc pd, const double *partials, int *ctr, double *scratch,
+                                                   bool plane, ProbState *st, const SolveParams &sp, int pass_index) {
+    const int lane = threadIdx.x & 31;
+    __threadfence();
+    if (lane == 0) *ctr = 0;  // ready for the next pass
+    const double2 *rows = reinterpret_cast<const double2 *>(partials + (int64_t)pd.blk_begin * kRowsPerBlock * kPart) + lane;
+    const int nrows = pd.blk_count * kRowsPerBlock;
+    double ax = 0.0, ay = 0.0;  // entries 2*lane, 2*lane + 1 of the summed Gram matrix; rows added in index order
+    int r = 0;
+    for (; r + 8 <= nrows; r += 8) {
+        double2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __ldcg(rows + (int64_t)(r + i) * (kPart / 2));  // written by other SMs
+#pragma unroll
+        for (int i = 0; i < 8; i++) { ax += v[i].x; ay += v[i].y; }
+    }
+    for (; r < nrows; r++) {
+        const double2 v = __ldcg(rows + (int64_t)r * (kPart / 2));
+        ax += v.x; ay += v.y;
+    }
+    __syncwarp();
+    double *D = scratch, *tot = scratch + kPart;
+    D[2 * lane] = ax; D[2 * lane + 1] = ay;
+    __syncwarp();
+    tot[lane] = slot_from_gram(D, plane, lane);
+    __syncwarp();
+    if (lane == 0) solve_from_totals(tot, (double)pd.npts, st, sp, pass_index);
 }
 
 // ---- pass, part B: the listed points of a part-A block, 32 searches at a time with every lane busy.  Each
@@ -366,9 +453,9 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
 template <int MODE>
 __global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b(
     GridDev G, const double *__restrict__ src_xyz, const BlockTask *__restrict__ tasks,
-    const ProbState *__restrict__ states, double *__restrict__ partials, int *__restrict__ corr_s,
-    NNCache *__restrict__ cache, const unsigned char *__restrict__ hard_ids, const int *__restrict__ hard_cnt,
-    PassParams pp) {
+    ProbState *states, double *partials, int *__restrict__ corr_s,
+    NNCache *__restrict__ cache, int *__restrict__ second_s, const unsigned char *__restrict__ hard_ids,
+    const int *__restrict__ hard_cnt, PassParams pp, const ProbDesc *__restrict__ probs, int *prob_ctr, SolveParams sp, int pass_index, int fuse_solve) {
     const int blk = blockIdx.x / kPassWarps, warp = blockIdx.x % kPassWarps, lane = threadIdx.x;
     const BlockTask task = tasks[blk];
     const ProbState *st = states + task.prob;
@@ -410,11 +497,12 @@ __global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b(
             if (fmaf(mz, mz, fmaf(my, my, mx * mx)) < 4.0f * pp.slack * pp.slack) slack = pp.slack;  // NaN: no
         }
         float sec = -1.0f;
+        int other = -1;
 #ifdef VB_SEARCH_COOP_ONLY
         const int bs = nn_search_warp(G, live, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, &d2);
 #else
         const int bs = nn_search_hybrid<32>(G, live, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, prior, ws.runs, &d2,
-                                            slack, &sec, VB_COOP_WARP_LANES);
+                                            slack, &sec, VB_COOP_WARP_LANES, &other);
 #endif
         if (live) {
             corr_s[slot] = bs;  // sorted position; vb200_batch_corr maps it to the caller's index
@@ -422,11 +510,22 @@ __global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b(
             m.qx = c.qx; m.qy = c.qy; m.qz = c.qz;
             m.sec = bs >= 0 ? sec : -1.0f;
             cache[slot] = m;
+            second_s[slot] = bs >= 0 ? other : -1;
             if (bs >= 0) ctx.row_of(bs, vs, pp.r2, x);
         }
         ctx.accumulate(ws.rows, x);
     }
-    ctx.write_partial(partials + ((int64_t)blk * kRowsPerBlock + kPassWarps + warp) * kPart);
+    ctx.write_partial(partials + ((int64_t)blk * kRowsPerBlock + 1 + warp) * kPart);
+    if (!fuse_solve) return;
+    // ---- iteration tail, fused: the LAST warp of a problem to get here (all of the problem's partial rows are
+    // then in memory) sums them in a fixed order and takes the estimator step — no separate solve launch.
+    __threadfence();
+    int prev = 0;
+    if (lane == 0) prev = atomicAdd(prob_ctr + task.prob, 1);
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    const ProbDesc pd = probs[task.prob];
+    if (prev != pd.blk_count * kPassWarps - 1) return;
+    iteration_tail(pd, partials, prob_ctr + task.prob, ws.rows, MODE == 1, states + task.prob, sp, pass_index);
 }
 
 // ---- estimator solves from the reduced slots ---------------------------------------------------------
@@ -434,8 +533,12 @@ __device__ void update_p2plane(const double *tot, const SolveParams &sp, double 
     mat4_identity(U);
     double JTJ[36], JTr[6];
     int k = 0;
-    for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+#pragma unroll
         for (int b = a; b < 6; b++) { JTJ[6 * a + b] = tot[k]; JTJ[6 * b + a] = tot[k]; k++; }
+    }
+#pragma unroll
     for (int a = 0; a < 6; a++) JTr[a] = tot[21 + a];
     if (sp.estimator == VB200_EST_P2PLANE) {
         double x[6];
@@ -480,38 +583,31 @@ __device__ void update_p2p(const double *tot, const double *cref, double *U) {
 // 32 estimator slots tot[kAcc] (shared memory); 256 threads.  Slot layout: point-to-plane 0..20 JTJ upper
 // triangle row-major, 21..26 JTr; point-to-point 0..2 sum s', 3..5 sum d', 6..14 sum d' s'^T, 15 sum |s'|^2;
 // both 30 = sum d2, 31 = count.
-__device__ __forceinline__ void reduce_partials(const ProbDesc &pd, const double *__restrict__ partials, bool plane,
+__device__ __forceinline__ void reduce_partials(const ProbDesc &pd, const double *__restrict__ partials,
+                                                const int *__restrict__ hard_cnt, bool plane,
                                                 double (*sw)[kPart], double *tot) {
     const int e = threadIdx.x & (kPart - 1), grp = threadIdx.x / kPart;  // 4 groups of 64 threads
     double s = 0.0;
-    for (int b = grp; b < pd.blk_count * kRowsPerBlock; b += 4)
-        s += partials[((int64_t)pd.blk_begin * kRowsPerBlock + b) * kPart + e];
+    // rows in index order per group.  (Skipping the part-B rows of blocks with an empty list was measured
+    // slower: the count lookup puts a dependent load in front of every row.)
+    (void)hard_cnt;
+    // 16 independent loads in flight per thread (the rows sit in L2; the chain of adds keeps its fixed order)
+    const double *col = partials + (int64_t)pd.blk_begin * kRowsPerBlock * kPart + e;
+    const int nrows = pd.blk_count * kRowsPerBlock;
+    int b = grp;
+    for (; b + 4 * 15 < nrows; b += 4 * 16) {
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = col[(int64_t)(b + 4 * i) * kPart];
+#pragma unroll
+        for (int i = 0; i < 16; i++) s += v[i];
+    }
+    for (; b < nrows; b += 4) s += col[(int64_t)b * kPart];
     sw[grp][e] = s;
     __syncthreads();
     if (threadIdx.x < kPart) sw[0][e] = ((sw[0][e] + sw[1][e]) + sw[2][e]) + sw[3][e];
     __syncthreads();
-    if (threadIdx.x < kAcc) {
-        const double *D = sw[0];
-        const int t = threadIdx.x;
-        double v = 0.0;
-        if (t == kSlotD2) v = D[63];
-        else if (t == kSlotCount) v = D[62];
-        else if (plane) {
-            if (t < 21) {
-                int a = 0, rem = t;
-                while (rem >= 6 - a) { rem -= 6 - a; ++a; }  // slot t = (a, b) of the upper triangle, b >= a
-                v = D[8 * a + a + rem];
-            } else if (t < 27) {
-                v = D[8 * (t - 21) + 6];
-            }
-        } else {
-            if (t < 3) v = D[8 * t + 6];
-            else if (t < 6) v = D[8 * t + 6];
-            else if (t < 15) v = D[8 * (3 + (t - 6) / 3) + (t - 6) % 3];
-            else if (t == 15) v = (D[0] + D[9]) + D[18];
-        }
-        tot[t] = v;
-    }
+    if (threadIdx.x < kAcc) tot[threadIdx.x] = slot_from_gram(sw[0], plane, threadIdx.x);
     __syncthreads();
 }
 
@@ -553,14 +649,14 @@ __device__ void solve_from_totals(const double *tot, double npts, ProbState *st,
 
 // One block per problem: reduce + solve (the single-GPU iteration tail).
 __global__ void __launch_bounds__(256) k_solve(const ProbDesc *__restrict__ probs, ProbState *__restrict__ states,
-                                               const double *__restrict__ partials, SolveParams sp,
-                                               int pass_index) {
+                                               const double *__restrict__ partials,
+                                               const int *__restrict__ hard_cnt, SolveParams sp, int pass_index) {
     const ProbDesc pd = probs[blockIdx.x];
     ProbState *st = states + blockIdx.x;
     if (st->done) return;
     __shared__ double sw[4][kPart];
     __shared__ double tot[kAcc];
-    reduce_partials(pd, partials, sp.estimator != VB200_EST_P2P, sw, tot);
+    reduce_partials(pd, partials, hard_cnt, sp.estimator != VB200_EST_P2P, sw, tot);
     if (threadIdx.x == 0) solve_from_totals(tot, (double)pd.npts, st, sp, pass_index);
 }
 
@@ -569,7 +665,8 @@ __global__ void __launch_bounds__(256) k_solve(const ProbDesc *__restrict__ prob
 // caller all-reduces across GPUs, k_solve_totals finishes the iteration from the combined totals.  Every rank
 // sees identical totals, hence applies the identical update: no broadcast of T is needed.
 __global__ void __launch_bounds__(256) k_reduce(const ProbDesc *__restrict__ probs, const ProbState *__restrict__ states,
-                                                const double *__restrict__ partials, bool plane,
+                                                const double *__restrict__ partials,
+                                                const int *__restrict__ hard_cnt, bool plane,
                                                 double *__restrict__ totals) {
     const ProbDesc pd = probs[blockIdx.x];
     __shared__ double sw[4][kPart];
@@ -577,7 +674,7 @@ __global__ void __launch_bounds__(256) k_reduce(const ProbDesc *__restrict__ pro
     if (states[blockIdx.x].done) {  // finished problems contribute their last totals unchanged
         return;
     }
-    reduce_partials(pd, partials, plane, sw, tot);
+    reduce_partials(pd, partials, hard_cnt, plane, sw, tot);
     if (threadIdx.x < kAcc) totals[(int64_t)blockIdx.x * kAcc + threadIdx.x] = tot[threadIdx.x];
 }
 
@@ -743,6 +840,7 @@ struct Batch {
     int *d_cloud_off = nullptr;
     // problems
     int P = 0;
+    bool all_nonempty = false;               // every problem has source points (the fused iteration tail needs one)
     std::vector<ProbDesc> probs;
     int nblk = 0;
     int64_t ncorr_slots = 0;
@@ -752,8 +850,10 @@ struct Batch {
     double *d_partials = nullptr;
     int *d_corr = nullptr;
     NNCache *d_cache = nullptr;              // per (problem, point): what its last search proved (k_pass_a/b)
+    int *d_second = nullptr;                 // ... and the runner-up kept with a two-candidate entry
     unsigned char *d_hard_ids = nullptr;     // per block and warp: the points part A left for part B
     int *d_hard_cnt = nullptr;
+    int *d_prob_ctr = nullptr;               // per problem: part-B warps finished in the current pass
     int64_t launches = 0;
     int iter_base = 0;                       // running pass index for vb200_batch_iterate
     double *d_totals = nullptr;              // P x kAcc, library-owned unless the caller supplied a buffer
@@ -767,8 +867,11 @@ static void batch_free_problems(Batch *b) {
     cudaStream_t st = b->scene->stream;
     void *ptrs[10] = {b->d_probs, b->d_states, b->d_tasks, b->d_partials, b->d_corr, b->d_totals, b->d_npts_global,
                       b->d_cache, b->d_hard_ids, b->d_hard_cnt};
+    if (b->d_prob_ctr) cudaFreeAsync(b->d_prob_ctr, st);
+    if (b->d_second) cudaFreeAsync(b->d_second, st);
+    b->d_second = nullptr;
     b->d_totals = nullptr; b->d_npts_global = nullptr; b->d_cache = nullptr;
-    b->d_hard_ids = nullptr; b->d_hard_cnt = nullptr;
+    b->d_hard_ids = nullptr; b->d_hard_cnt = nullptr; b->d_prob_ctr = nullptr;
     for (void *q : ptrs)
         if (q) cudaFreeAsync(q, st);
     b->d_probs = nullptr; b->d_states = nullptr; b->d_tasks = nullptr; b->d_partials = nullptr; b->d_corr = nullptr;
@@ -865,6 +968,15 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
     }
     b->nblk = (int)tasks.size();
     b->ncorr_slots = corr;
+    // Fusing the iteration tail into part B (its last warp per problem reduces + solves) was measured SLOWER
+    // than a separate k_solve launch: one warp summing ~800 partial rows is latency-bound (~50 us vs ~25 us).
+    // The code path stays for experiments (-DVB_FUSE_SOLVE).
+#ifdef VB_FUSE_SOLVE
+    b->all_nonempty = P > 0;
+    for (int p = 0; p < P; p++) b->all_nonempty = b->all_nonempty && b->probs[p].npts > 0;
+#else
+    b->all_nonempty = false;
+#endif
     VB_CUDA(cudaMallocAsync((void **)&b->d_probs, sizeof(ProbDesc) * (size_t)std::max(P, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_states, sizeof(ProbState) * (size_t)std::max(P, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_tasks, sizeof(BlockTask) * (size_t)std::max(b->nblk, 1), st));
@@ -879,27 +991,38 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
     VB_CUDA(cudaMemsetAsync(b->d_corr, 0xff, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_cache, sizeof(NNCache) * (size_t)std::max<int64_t>(corr, 1), st));
     VB_CUDA(cudaMemsetAsync(b->d_cache, 0xff, sizeof(NNCache) * (size_t)std::max<int64_t>(corr, 1), st));  // NaN
+    VB_CUDA(cudaMallocAsync((void **)&b->d_second, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
+    VB_CUDA(cudaMemsetAsync(b->d_second, 0xff, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_hard_ids, (size_t)kChunk * (size_t)std::max(b->nblk, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_hard_cnt, sizeof(int) * kPassWarps * (size_t)std::max(b->nblk, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_prob_ctr, sizeof(int) * (size_t)std::max(P, 1), st));
+    VB_CUDA(cudaMemsetAsync(b->d_prob_ctr, 0, sizeof(int) * (size_t)std::max(P, 1), st));
     VB_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
     return VB200_OK;
 }
 
 
-// one correspondence pass = part A (every point, streaming) + part B (the points that need a search)
-static void launch_pass(Batch *b, bool plane, const PassParams &pp) {
+// one correspondence pass = part A (every point, streaming) + part B (the points that need a search).  With
+// `sp` given, part B also finishes the iteration (reduction + estimator step by each problem's last warp).
+static void launch_pass(Batch *b, bool plane, const PassParams &pp, const SolveParams *sp = nullptr, int pass_index = 0) {
     Scene *sc = b->scene;
     cudaStream_t st = sc->stream;
+    SolveParams s0;
+    memset(&s0, 0, sizeof(s0));
+    const SolveParams &s = sp ? *sp : s0;
+    const int fuse = sp ? 1 : 0;
     if (plane) {
         k_pass_a<1><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
-                                                  b->d_cache, b->d_hard_ids, b->d_hard_cnt, pp);
-        k_pass_b<1><<<b->nblk * kPassWarps, 32, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
-                                                  b->d_cache, b->d_hard_ids, b->d_hard_cnt, pp);
+                                                  b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp);
+        k_pass_b<1><<<b->nblk * kPassWarps, 32, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials,
+                                                         b->d_corr, b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp,
+                                                         b->d_probs, b->d_prob_ctr, s, pass_index, fuse);
     } else {
         k_pass_a<0><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
-                                                  b->d_cache, b->d_hard_ids, b->d_hard_cnt, pp);
-        k_pass_b<0><<<b->nblk * kPassWarps, 32, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
-                                                  b->d_cache, b->d_hard_ids, b->d_hard_cnt, pp);
+                                                  b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp);
+        k_pass_b<0><<<b->nblk * kPassWarps, 32, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials,
+                                                         b->d_corr, b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp,
+                                                         b->d_probs, b->d_prob_ctr, s, pass_index, fuse);
     }
     b->launches += 2;
 }
@@ -927,11 +1050,14 @@ static int batch_run(Batch *b, int estimator, const double *gravity, double max_
         for (int a = 0; a < 3; a++) sp.g[a] = gravity[a] / l;
     }
     for (int it = 0; it <= max_iter; it++) {
-        if (b->nblk) {
-            launch_pass(b, plane, pp);
+        if (b->all_nonempty) {
+            launch_pass(b, plane, pp, &sp, it);
+        } else {
+            // a problem without source points has no part-B warp to finish it: separate solve launch
+            if (b->nblk) launch_pass(b, plane, pp);
+            k_solve<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, b->d_hard_cnt, sp, it);
+            b->launches++;
         }
-        k_solve<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, sp, it);
-        b->launches++;
     }
     VB_CUDA(cudaGetLastError());
     return VB200_OK;
@@ -971,7 +1097,7 @@ static int batch_pass(Batch *b, int estimator, double max_dist) {
     if (b->nblk) {
         launch_pass(b, estimator != VB200_EST_P2P, pp);
     }
-    k_reduce<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, estimator != VB200_EST_P2P, totals);
+    k_reduce<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, b->d_hard_cnt, estimator != VB200_EST_P2P, totals);
     b->launches++;
     VB_CUDA(cudaGetLastError());
     return VB200_OK;
@@ -1028,11 +1154,16 @@ static int batch_iterate(Batch *b, int estimator, const double *gravity, double 
     const bool timed = n_iter == 1;  // per-kernel events only make sense around a single iteration
     for (int it = 0; it < n_iter; it++) {
         if (timed) VB_CUDA(cudaEventRecord(b->ev[0], st));
-        launch_pass(b, plane, pp);
-        if (timed) VB_CUDA(cudaEventRecord(b->ev[1], st));
-        k_solve<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, sp, b->iter_base++);
+        if (b->all_nonempty) {
+            launch_pass(b, plane, pp, &sp, b->iter_base++);
+            if (timed) VB_CUDA(cudaEventRecord(b->ev[1], st));
+        } else {
+            launch_pass(b, plane, pp);
+            if (timed) VB_CUDA(cudaEventRecord(b->ev[1], st));
+            k_solve<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, b->d_hard_cnt, sp, b->iter_base++);
+            b->launches += 1;
+        }
         if (timed) VB_CUDA(cudaEventRecord(b->ev[2], st));
-        b->launches += 1;
     }
     b->ev_valid = timed;
     VB_CUDA(cudaGetLastError());

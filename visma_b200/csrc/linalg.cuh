@@ -29,66 +29,114 @@ __device__ inline void mat4_mul(const double *A, const double *B, double *C) {
     for (int i = 0; i < 16; i++) C[i] = R[i];
 }
 
+// Both factorizations below pivot, but are written with compile-time indices only (every loop unrolled, a
+// row / column exchange expressed as predicated element swaps over the static candidates): the matrices stay
+// in registers instead of local memory, which is what made the one-thread solve the longest part of k_solve.
+__device__ __forceinline__ void cswap(bool c, double &a, double &b) {
+    const double t = a;
+    a = c ? b : a;
+    b = c ? t : b;
+}
+
 // determinant of an n x n matrix (n <= 6) by Gaussian elimination with partial pivoting
 template <int N>
-__device__ inline double det_lu(const double *A) {
+__device__ __forceinline__ double det_lu(const double *A) {
     double M[N * N];
+#pragma unroll
     for (int i = 0; i < N * N; i++) M[i] = A[i];
     double det = 1.0;
+    bool singular = false;
+#pragma unroll
     for (int c = 0; c < N; c++) {
         int p = c;
-        for (int r = c + 1; r < N; r++)
-            if (fabs(M[N * r + c]) > fabs(M[N * p + c])) p = r;
-        if (M[N * p + c] == 0.0) return 0.0;
-        if (p != c) {
-            for (int k = 0; k < N; k++) {
-                double t = M[N * c + k];
-                M[N * c + k] = M[N * p + k];
-                M[N * p + k] = t;
-            }
-            det = -det;
-        }
-        det *= M[N * c + c];
+        double best = fabs(M[N * c + c]);
+#pragma unroll
         for (int r = c + 1; r < N; r++) {
-            double f = M[N * r + c] / M[N * c + c];
+            const double v = fabs(M[N * r + c]);
+            if (v > best) { best = v; p = r; }
+        }
+#pragma unroll
+        for (int r = c + 1; r < N; r++) {
+#pragma unroll
+            for (int k = 0; k < N; k++) cswap(p == r, M[N * c + k], M[N * r + k]);
+        }
+        if (p != c) det = -det;
+        const double piv = M[N * c + c];
+        if (piv == 0.0) singular = true;
+        det *= piv;
+#pragma unroll
+        for (int r = c + 1; r < N; r++) {
+            const double f = M[N * r + c] / piv;
+#pragma unroll
             for (int k = c; k < N; k++) M[N * r + k] -= f * M[N * c + k];
         }
     }
-    return det;
+    return singular ? 0.0 : det;
 }
 
 // x = A^-1 b for symmetric A by LDL^T with diagonal pivoting (what Eigen's A.ldlt().solve(b) computes)
 template <int N>
-__device__ inline void ldlt_solve(const double *A, const double *b, double *x) {
+__device__ __forceinline__ void ldlt_solve(const double *A, const double *b, double *x) {
     double M[N * N], y[N];
-    int perm[N];
+    int piv[N];
+#pragma unroll
     for (int i = 0; i < N * N; i++) M[i] = A[i];
-    for (int i = 0; i < N; i++) perm[i] = i;
+#pragma unroll
+    for (int i = 0; i < N; i++) y[i] = b[i];
+#pragma unroll
     for (int k = 0; k < N; k++) {
         int p = k;
-        for (int i = k + 1; i < N; i++)
-            if (fabs(M[N * i + i]) > fabs(M[N * p + p])) p = i;
-        if (p != k) {
-            for (int c = 0; c < N; c++) { double t = M[N * k + c]; M[N * k + c] = M[N * p + c]; M[N * p + c] = t; }
-            for (int r = 0; r < N; r++) { double t = M[N * r + k]; M[N * r + k] = M[N * r + p]; M[N * r + p] = t; }
-            int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+        double best = fabs(M[N * k + k]);
+#pragma unroll
+        for (int i = k + 1; i < N; i++) {
+            const double v = fabs(M[N * i + i]);
+            if (v > best) { best = v; p = i; }
         }
-        double d = M[N * k + k];
-        if (d == 0.0) continue;
-        for (int i = k + 1; i < N; i++) M[N * i + k] /= d;
-        for (int i = k + 1; i < N; i++)
-            for (int j = k + 1; j <= i; j++) {
-                M[N * i + j] -= M[N * i + k] * d * M[N * j + k];
-                M[N * j + i] = M[N * i + j];
+        piv[k] = p;
+        // symmetric exchange of rows and columns k <-> p, and of the right-hand side
+#pragma unroll
+        for (int i = k + 1; i < N; i++) {
+            const bool sw = p == i;
+#pragma unroll
+            for (int c = 0; c < N; c++) cswap(sw, M[N * k + c], M[N * i + c]);
+#pragma unroll
+            for (int r = 0; r < N; r++) cswap(sw, M[N * r + k], M[N * r + i]);
+            cswap(sw, y[k], y[i]);
+        }
+        const double d = M[N * k + k];
+        if (d != 0.0) {
+#pragma unroll
+            for (int i = k + 1; i < N; i++) M[N * i + k] /= d;
+#pragma unroll
+            for (int i = k + 1; i < N; i++) {
+#pragma unroll
+                for (int j = k + 1; j <= i; j++) {
+                    M[N * i + j] -= M[N * i + k] * d * M[N * j + k];
+                    M[N * j + i] = M[N * i + j];
+                }
             }
+        }
     }
-    for (int i = 0; i < N; i++) y[i] = b[perm[i]];
-    for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+#pragma unroll
         for (int j = 0; j < i; j++) y[i] -= M[N * i + j] * y[j];
+    }
+#pragma unroll
     for (int i = 0; i < N; i++) y[i] = (M[N * i + i] != 0.0) ? y[i] / M[N * i + i] : 0.0;
-    for (int i = N - 1; i >= 0; i--)
+#pragma unroll
+    for (int i = N - 1; i >= 0; i--) {
+#pragma unroll
         for (int j = i + 1; j < N; j++) y[i] -= M[N * j + i] * y[j];
-    for (int i = 0; i < N; i++) x[perm[i]] = y[i];
+    }
+    // undo the exchanges, last first
+#pragma unroll
+    for (int k = N - 1; k >= 0; k--) {
+#pragma unroll
+        for (int i = k + 1; i < N; i++) cswap(piv[k] == i, y[k], y[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = y[i];
 }
 
 // SolveLinearSystem(JTJ, -JTr): false when |det| < 1e-6 or non-finite (Utility/Eigen.cpp:41-52)
