@@ -12,7 +12,10 @@ with no data-path collective; one all-gather of the final poses), so per-GPU wor
           on the library's stream, L2 flushed (untimed) before every step, max over ranks.
   e2e     the public C-ABI call vb200_icp_run with HOST buffers (pinned): H2D of the 32 sources, the spatial
           sort, 30 iterations, D2H of the poses, every call; iterations/s = 30 / call time.
-  roofline  k_pass (the correspondence + reduction kernel): SURVEY §8d algorithmic bytes / its measured time.
+  roofline  the correspondence pass (k_pass_a: every point, cached-neighbour test + estimator sums; k_pass_b:
+            the points that need a search): SURVEY §8d algorithmic bytes / its measured time, averaged over
+            the K timed iterations of the trajectory from the initial poses (the settled iterations alone are
+            reported beside it in config.pass_ms_last3 and roofline.settled).
   cpu_baseline  the unmodified reference (oracle/_ref) on a bounded sample of the same workload.
 """
 import argparse
@@ -55,11 +58,12 @@ def measured_peak():
 
 
 def profiled_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_pass launch from the latest committed ncu capture."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of one correspondence pass (k_pass_a + k_pass_b launches of
+    one settled iteration) from the latest committed ncu captures."""
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            t = json.load(f)["k_pass"]
-        return int(t["dram_bytes_read"] + t["dram_bytes_write"])
+            t = json.load(f)
+        return int(sum(t[k]["dram_bytes_read"] + t[k]["dram_bytes_write"] for k in ("k_pass_a", "k_pass_b")))
     except Exception:
         return None
 
@@ -151,6 +155,12 @@ def run_reference(args):
         reference_sample(d, n_s)
     ts = [reference_sample(d, n_s) for _ in range(args.steps)]
     t = float(np.mean(ts))
+    # informational: one object with the reference's default criteria (stops at convergence)
+    t1 = time.perf_counter()
+    src, sn = d["sources"][0]
+    pyref.registration_icp(src, d["scene_xyz"], MAX_DIST, d["T_init"][0], pyref.P2PLANE, src_nrm=sn,
+                           tgt_nrm=d["scene_nrm"])
+    t_def = time.perf_counter() - t1
     # one sample = ICP_ITERS iterations of n_s objects; a full iteration covers N_OBJ objects
     value = ICP_ITERS / (t * N_OBJ / n_s)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -164,6 +174,9 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
                              "sample": "%d of 32 objects per step, x%d steps, scaled to 32" % (n_s, args.steps)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "default_criteria": {"s_per_object": t_def, "s_per_32_objects": t_def * N_OBJ,
+                                 "note": "open3d::RegistrationICP with ICPConvergenceCriteria() defaults on object 0 "
+                                         "(tree build included); informational"},
             "gpu_launches": 0}
     emit(line)
 
@@ -200,7 +213,7 @@ def run_ours(args):
     def one_step(timed):
         flush.fill_(rank + 1)           # untimed: evict L2 between timed iterations
         torch.cuda.synchronize()
-        batch.iterate(est, MAX_DIST, 1)  # k_pass + k_solve, recorded by the library's own events
+        batch.iterate(est, MAX_DIST, 1)  # k_pass_a + k_pass_b + k_solve, recorded by the library's own events
         p_ms, s_ms = batch.last_kernel_ms()
         return p_ms, s_ms
 
@@ -243,6 +256,14 @@ def run_ours(args):
     total_ms = float(t.item())
     value = world * args.steps / (total_ms * 1e-3)
 
+    # ablation (informational): the same trajectory with the cached-neighbour test off — every point searched
+    # in every pass, the previous match used only as a search bound
+    os.environ["VB200_NN_CACHE"] = "0"
+    batch.set_problems(d["T_init"])
+    abl = [sum(one_step(True)) for _ in range(args.steps)]
+    del os.environ["VB200_NN_CACHE"]
+    abl_ms = float(np.mean(abl))
+
     # the real loop, back to back without flushes (informational: what one RegistrationICP run costs)
     batch.set_problems(d["T_init"])
     torch.cuda.synchronize()
@@ -275,6 +296,18 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * ICP_ITERS / float(te.item())
+    # informational: the same call with the reference's DEFAULT criteria (ICPConvergenceCriteria(): stop when
+    # fitness and rmse change by < 1e-6, Registration.h:49-50) — what one real RegistrationICP run of the
+    # 32 objects costs end to end, and how many iterations it takes
+    crit_def = reg.ICPConvergenceCriteria()
+    reg.RegistrationICPBatch(None, scene, MAX_DIST, d["T_init"], est, crit_def, want_corr=False, packed=packed)
+    t_def = []
+    for _ in range(5):
+        t1 = time.perf_counter()
+        r_def = reg.RegistrationICPBatch(None, scene, MAX_DIST, d["T_init"], est, crit_def, want_corr=False,
+                                         packed=packed)
+        t_def.append(time.perf_counter() - t1)
+    def_iters = [int(r.iterations_) for r in r_def]
     clocks = sampler.stop()
 
     # sanity: the timed work converged to the ground truth (guards against timing a no-op)
@@ -287,6 +320,7 @@ def run_ours(args):
         peak, how = measured_peak()
         b_alg = algorithmic_bytes(N_SCENE, N_OBJ * M_PTS, k_total, N_OBJ)
         p_ms = float(np.mean(pass_ms))
+        p_settled = float(np.mean(pass_ms[-max(1, len(pass_ms) // 3):]))
         achieved = b_alg / (p_ms * 1e-3) / 1e9
         cpu = None
         if not args.no_cpu_baseline:
@@ -326,7 +360,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "2M-pt synthetic room scene x 32 chair fragments x 50k pts per GPU, "
                                    "point-to-plane, max_dist 0.075; step = 1 ICP iteration of all 32 objects "
-                                   "(k_pass + k_solve)",
+                                   "(k_pass_a + k_pass_b + k_solve), trajectory replayed from the initial poses",
                        "n_scene": N_SCENE, "objects_per_gpu": N_OBJ, "pts_per_object": M_PTS,
                        "l2": "256 MiB flush before every timed step (untimed)",
                        "back_to_back_ms_per_iteration_no_flush": loop_ms,
@@ -334,6 +368,9 @@ def run_ours(args):
                        "pass_ms_last3": [round(float(x), 4) for x in pass_ms[-3:]],
                        "pass_ms_per_step": [round(float(x), 3) for x in pass_ms],
                        "solve_ms": float(np.mean(solve_ms)), "allgather_ms": ag_ms,
+                       "ablation_search_every_point_every_pass": {
+                           "ms_per_step": abl_ms, "iterations_per_s": world * 1e3 / abl_ms,
+                           "note": "VB200_NN_CACHE=0: no cached-neighbour test; same results"},
                        "scene_build_s": scene_build_s, "converged_to_ground_truth": ok,
                        "max_pose_err_rad_m": [float(errs[:, 0].max()), float(errs[:, 1].max())]},
             "e2e": {"value": e2e_value, "unit": UNIT,
@@ -343,11 +380,20 @@ def run_ours(args):
                             "(mean of %d; min %.2f, median %.2f, max %.2f)"
                             % (e2e_s * 1e3, n_e2e, min(e2e_calls) * 1e3, float(np.median(e2e_calls)) * 1e3,
                                max(e2e_calls) * 1e3)},
+            "e2e_default_criteria": {"ms_per_call_32_objects": float(np.median(t_def)) * 1e3,
+                                     "iterations_min_mean_max": [min(def_iters), float(np.mean(def_iters)),
+                                                                 max(def_iters)],
+                                     "note": "vb200_icp_run with ICPConvergenceCriteria() defaults (1e-6, 1e-6, 30): "
+                                             "the loop stops once every object has converged; informational"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_pass<point-to-plane>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(), "peak_source": how,
-                         "algorithmic_bytes": b_alg},
+            "roofline": {"kernel": "k_pass_a + k_pass_b <point-to-plane> (one correspondence pass)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": profiled_traffic(), "peak_source": how, "algorithmic_bytes": b_alg,
+                         "settled": {"pass_ms": p_settled, "achieved": b_alg / (p_settled * 1e-3) / 1e9,
+                                     "frac": b_alg / (p_settled * 1e-3) / 1e9 / peak,
+                                     "note": "mean of the last third of the timed iterations (cached-neighbour "
+                                             "regime: part A streams, part B nearly empty)"}},
             "cpu_baseline": cpu,
         }
         emit(line)

@@ -706,12 +706,30 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
     float bound = r2_ub;  // f32 distance of a real candidate, when one is known
     float thr = (kLaneProbeRho * g.fine) * (kLaneProbeRho * g.fine);  // no bound yet: probe the nearest cells
     int mode = valid ? kScan : kDone;
-    if (valid && prior >= 0) {
-        const float4 t = __ldg(G.hi + prior);
+    {
+        // Bound = distance to the nearest of the WARP's previous matches, not just the lane's own.  Under a rigid
+        // move the points of a patch slide together: a point that has moved a centimetre along the surface is
+        // now nearest to what was its lane neighbour's match, and its own old match would give twice the reach
+        // (eight times the cells).  The lanes of a warp are spatial neighbours, so their 32 old matches are the
+        // scene points around the query — 32 candidate bounds for ~10 instructions each.
+        float4 t = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.0f);
+        if (valid && prior >= 0) t = __ldg(G.hi + prior);
+#ifndef VB_NO_NEIGHBOUR_BOUNDS
+        unsigned have = __ballot_sync(FULL, valid && prior >= 0);
+        float nb = 3.0e38f;
+        while (have) {
+            const int j = __ffs(have) - 1;
+            have &= have - 1u;
+            const float dx = c.qx - __shfl_sync(FULL, t.x, j), dy = c.qy - __shfl_sync(FULL, t.y, j),
+                        dz = c.qz - __shfl_sync(FULL, t.z, j);
+            nb = fminf(nb, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        }
+#else
         const float dx = c.qx - t.x, dy = c.qy - t.y, dz = c.qz - t.z;
-        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d < r2_ub) {
-            bound = d;
+        const float nb = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+#endif
+        if (valid && nb < r2_ub) {
+            bound = nb;
             thr = reach_of(g, bound, r2_ub);
             if (thr > max_reach2) { mode = kCoop; VB_STAT(4, 1); }
             else thr = widen(thr, slack, max_reach2);

@@ -20,6 +20,7 @@
 //   - reductions have a fixed order (warp halving tree -> warps -> blocks), so results are deterministic;
 //     the reference's OpenMP merge order is thread-arrival order.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -79,6 +80,7 @@ struct PassParams {
     float r2_ub;    // f32 upper bound of r2 including the screening band
     float slack;    // how far beyond the answer's reach a search looks, so that its result survives small moves
     float pos_err;  // bound on the error of a distance between two centred-f32 query positions
+    int use_cache;  // 0: every point is searched in every pass (dev knob VB200_NN_CACHE=0: the ablation bench.py reports)
 };
 
 #ifndef VB_SLACK_PCT
@@ -90,6 +92,8 @@ inline PassParams make_pass_params(const GridParams &g, double max_dist) {
     pp.r2_ub = r2_upper_bound(g, pp.r2);
     pp.slack = g.fine * (VB_SLACK_PCT * 0.01f);
     pp.pos_err = g.band_a;  // band_a = 2 sqrt(3) e with e the per-axis error of such a difference: a 2x margin
+    const char *nc = getenv("VB200_NN_CACHE");
+    pp.use_cache = !(nc && nc[0] == '0');
     return pp;
 }
 
@@ -324,7 +328,7 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
             } else {
                 hard = true;
 #ifndef VB_NO_NN_CACHE
-                const int prior = corr_s[slot];
+                const int prior = pp.use_cache ? corr_s[slot] : -1;
                 if (prior >= 0) {
                     const NNCache m = cache[slot];
                     const float4 t = __ldg(G.hi + prior);
@@ -371,6 +375,8 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
             VB_STAT(14, hard && pr >= 0 && !(cache[task.corr_begin + local].sec >= 0.0f));
         }
 #endif
+        // (Prefetching the next batch's streams and the match's rows ahead of the arithmetic was measured
+        // slower — 0.089 vs 0.084 ms for a settled pass: at 48 warps per SM the gathers already overlap.)
         const unsigned hm = __ballot_sync(0xffffffffu, hard);
         if (hard) my_hard[nhard + __popc(hm & ((1u << lane) - 1u))] = (unsigned char)(k * 32 + lane);
         nhard += __popc(hm);
