@@ -12,6 +12,12 @@ for est in (reg.TransformationEstimationPointToPlane(), reg.TransformationEstima
             reg.TransformationEstimationPointToPlaneGravity()):
     r = reg.RegistrationICPBatch(cl, sc, 0.075, d["T_init"], est)
     print(type(est).__name__, [round(x.fitness_, 4) for x in r])
+# a long run past convergence: the cached-neighbour test, two-candidate entries and near-empty part-B lists
+b = reg.Batch(sc, cl)
+b.set_problems(d["T_init"])
+b.iterate(reg.TransformationEstimationPointToPlane(), 0.075, 25)
+print("iterate", [round(x.fitness_, 4) for x in b.results()])
+b.close()
 i, d2 = sc.SearchHybrid1(synth.knn_queries(d["scene_xyz"], 3000), 0.075)
 print("knn matched", int((i >= 0).sum()))
 print("register", reg.RegisterModelToScene(cl[0], sc, 4, 0.05, True)["ncorr"])

@@ -165,6 +165,7 @@ struct __align__(16) WarpScratch {
 };
 constexpr int kPart = 64;  // doubles per warp partial: the 8x8 Gram matrix of the staged rows
 static_assert(32 * kPtsPerThread <= 256, "hard_ids holds a warp's point ids in one byte");
+static_assert(kPassTpb == kPassWarps * 32 && kPassWarps * (kPart / 2) == kPassTpb, "k_pass_a zeroes part B's rows with one store per thread");
 
 // D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor cores (DMMA).  Lane l holds A[l>>2][l&3], B[l&3][l>>2] and
 // D[l>>2][2(l&3) + {0,1}].
@@ -385,16 +386,24 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
     if (lane == 0) hard_cnt[blockIdx.x * kPassWarps + warp] = nhard;
     // one partial row per block: the warps' Gram matrices summed in warp order (rows_sh is free again)
     const double2 mine = ctx.lane_pair();
+    __shared__ int listed[kPassWarps];
     __syncthreads();
     double2 *red = reinterpret_cast<double2 *>(&rows_sh[0][0]);
     red[warp * 32 + lane] = mine;
+    if (lane == 0) listed[warp] = nhard;
     __syncthreads();
+    double2 *out = reinterpret_cast<double2 *>(partials + (int64_t)blockIdx.x * kRowsPerBlock * kPart);
     if (warp == 0) {
         double2 t = red[lane];
 #pragma unroll
         for (int w = 1; w < kPassWarps; w++) { t.x += red[w * 32 + lane].x; t.y += red[w * 32 + lane].y; }
-        reinterpret_cast<double2 *>(partials + (int64_t)blockIdx.x * kRowsPerBlock * kPart)[lane] = t;
+        out[lane] = t;
     }
+    // nothing listed: part B's warps for this block exit on their first load, so their rows are zeroed here
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < kPassWarps; w++) total += listed[w];
+    if (total == 0) out[(kPart / 2) + threadIdx.x] = make_double2(0.0, 0.0);  // 4 rows x 32 double2 = 128 threads
 }
 
 // entry t of the 32 estimator slots from a summed 8x8 Gram matrix D.  Slot layout: point-to-plane 0..20 JTJ
@@ -463,9 +472,6 @@ __global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b(
     NNCache *__restrict__ cache, int *__restrict__ second_s, const unsigned char *__restrict__ hard_ids,
     const int *__restrict__ hard_cnt, PassParams pp, const ProbDesc *__restrict__ probs, int *prob_ctr, SolveParams sp, int pass_index, int fuse_solve) {
     const int blk = blockIdx.x / kPassWarps, warp = blockIdx.x % kPassWarps, lane = threadIdx.x;
-    const BlockTask task = tasks[blk];
-    const ProbState *st = states + task.prob;
-    if (st->done) return;
     // the block's list = its warps' lists of part A, concatenated
     int seg_end[kPassWarps];
     int total = 0;
@@ -474,6 +480,12 @@ __global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b(
         total += hard_cnt[blk * kPassWarps + w];
         seg_end[w] = total;
     }
+    // Nothing to search (most blocks once an alignment settles): part A has zeroed this warp's partial row.
+    // (hard_cnt of a finished problem is stale; its rows are never read again, so either exit is fine.)
+    if (total == 0 && !fuse_solve) return;
+    const BlockTask task = tasks[blk];
+    const ProbState *st = states + task.prob;
+    if (st->done) return;
     __shared__ WarpScratch ws;
     PassCtx<MODE> ctx(G, st->T);
 #pragma unroll 1
