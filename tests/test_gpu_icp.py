@@ -329,3 +329,31 @@ def test_cache_survives_set_problems_and_tiny_moves(vb, scene):
         for g, w in zip(got, want):
             assert np.array_equal(g.correspondence_set_, w.correspondence_set_)
         b2.close()
+
+
+def test_exact_ties_through_the_cached_path(vb, scene):
+    """Every scene point twice: each query's winner and runner-up are at EXACTLY the same distance, so every
+    decision goes through the tie rule (lowest original index) — in the search, in the two-candidate cache
+    entries and in part A's test.  The running batch must agree with the warp-per-query KNN at every iteration."""
+    xyz = np.concatenate([scene["scene_xyz"][:40000], scene["scene_xyz"][:40000]])
+    nrm = np.concatenate([scene["scene_nrm"][:40000], scene["scene_nrm"][:40000]])
+    sc = vb.reg.Scene(vb.reg.PointCloud(xyz, nrm), 0.075)
+    cl = clouds(vb, scene)[:2]
+    est = vb.reg.TransformationEstimationPointToPlane()
+    run = vb.reg.Batch(sc, cl)
+    T = np.array(scene["T_init"][:2], dtype=np.float64)
+    run.set_problems(T)
+    for it in range(10):
+        run.iterate(est, 0.075, 1)
+        got = run.results(want_corr=True)
+        for b in range(2):
+            q = cl[b].points_ @ T[b][:3, :3].T + T[b][:3, 3]
+            idx, _ = sc.SearchHybrid1(q, 0.075)
+            full = -np.ones(len(q), np.int64)
+            cs = got[b].correspondence_set_
+            full[cs[:, 0]] = cs[:, 1]
+            # the transform is applied with FMAs on the device and without in numpy: a query may differ in the
+            # last bit, which can only matter for a point exactly on the radius — none here
+            assert np.array_equal(full, idx), (it, b, int((full != idx).sum()))
+            assert (idx[idx >= 0] < 40000).all()      # ties went to the first copy
+        T = np.stack([r.transformation_ for r in got])
