@@ -753,13 +753,31 @@ __global__ void __launch_bounds__(256) k_src_scatter(const double *__restrict__ 
     sidx[start[kk] + atomicAdd(cursor + kk, 1)] = ((sz * 4 + sy * 2 + sx) << kSubShift) | i;
 }
 
-// one WARP per bucket (most of the ncloud x 32768 buckets are empty and exit at once)
-__global__ void __launch_bounds__(256) k_src_sort_buckets(int nbuckets, const int *__restrict__ start,
-                                                          int *__restrict__ sidx) {
-    const int b = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (b >= nbuckets) return;
-    const int s0 = start[b], s1 = start[b + 1];
-    if (s1 - s0 > 1) warp_cell_sort<int, 8>(sidx + s0, s1 - s0);
+// Most of the ncloud x 32768 buckets are empty (a warp per bucket spent 0.34 ms on finding that out): one thread
+// per bucket lists the ones holding more than one point (any order: every bucket is sorted on its own) ...
+__global__ void __launch_bounds__(256) k_src_list_buckets(int nbuckets, const int *__restrict__ start,
+                                                          int *__restrict__ list, int *__restrict__ nlist) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool need = b < nbuckets && start[b + 1] - start[b] > 1;
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(nlist, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (need) list[base + __popc(m & ((1u << lane) - 1u))] = b;
+}
+
+// ... and a fixed grid of warps sorts the listed buckets
+__global__ void __launch_bounds__(256) k_src_sort_buckets(const int *__restrict__ list, const int *__restrict__ nlist,
+                                                          const int *__restrict__ start, int *__restrict__ sidx) {
+    const int n = *nlist;
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < n; i += nwarps) {
+        const int b = list[i];
+        const int s0 = start[b], s1 = start[b + 1];
+        warp_cell_sort<int, 8>(sidx + s0, s1 - s0);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_src_gather(const double *__restrict__ in, int n,
@@ -852,6 +870,7 @@ __global__ void __launch_bounds__(256) k_estimate_solve(const double *__restrict
 // ======================================================================================================
 struct Batch {
     Scene *scene = nullptr;
+    cudaStream_t stream = nullptr;  // the scene's stream, or its second one (vb200_icp_run pipelines two halves)
     int ncloud = 0;
     int64_t npts = 0;
     std::vector<int> cloud_off;     // host copy, ncloud+1
@@ -886,7 +905,7 @@ struct Batch {
 };
 
 static void batch_free_problems(Batch *b) {
-    cudaStream_t st = b->scene->stream;
+    cudaStream_t st = b->stream;
     void *ptrs[10] = {b->d_probs, b->d_states, b->d_tasks, b->d_partials, b->d_corr, b->d_totals, b->d_npts_global,
                       b->d_cache, b->d_hard_ids, b->d_hard_cnt};
     if (b->d_prob_ctr) cudaFreeAsync(b->d_prob_ctr, st);
@@ -907,7 +926,7 @@ static void batch_free(Batch *b) {
     batch_free_problems(b);
     for (int i = 0; i < 3; i++)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);
-    cudaStream_t st = b->scene->stream;
+    cudaStream_t st = b->stream;
     void *ptrs[3] = {b->d_src, b->d_src_orig, b->d_cloud_off};
     for (void *q : ptrs)
         if (q) cudaFreeAsync(q, st);
@@ -916,7 +935,7 @@ static void batch_free(Batch *b) {
 
 static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int ncloud) {
     Scene *sc = b->scene;
-    cudaStream_t st = sc->stream;
+    cudaStream_t st = b->stream;
     if (ncloud > 32768) return VB200_ERR_INVALID;  // bucket table = ncloud x 32768 counters (int indexed)
     b->ncloud = ncloud;
     b->cloud_off.resize((size_t)ncloud + 1);
@@ -949,16 +968,19 @@ static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int
     VB_TRY(exclusive_scan_i32(d_counts.p, d_start.p, (int64_t)nb, nullptr, st));
     VB_CUDA(cudaMemsetAsync(d_counts.p, 0, sizeof(int) * nb, st));
     k_src_scatter<<<div_up(n, 256), 256, 0, st>>>(d_in.p, d_key.p, n, 4.0 / sc->grid.p.cell, d_start.p, d_counts.p, d_sidx.p);
-    k_src_sort_buckets<<<div_up(((int64_t)nb - 1) * 32, 256), 256, 0, st>>>((int)nb - 1, d_start.p, d_sidx.p);
+    // the key array is free once the scatter has run: it becomes the list of buckets to sort (at most n / 2)
+    VB_CUDA(cudaMemsetAsync(d_counts.p, 0, sizeof(int), st));
+    k_src_list_buckets<<<div_up((int64_t)nb - 1, 256), 256, 0, st>>>((int)nb - 1, d_start.p, d_key.p, d_counts.p);
+    k_src_sort_buckets<<<kNumSMsB200 * 8, 256, 0, st>>>(d_key.p, d_counts.p, d_start.p, d_sidx.p);
     k_src_gather<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, d_sidx.p, b->d_cloud_off, ncloud, b->d_src, b->d_src_orig);
     VB_CUDA(cudaGetLastError());
-    b->launches += 4 + 3;
+    b->launches += 5 + 3;
     VB_CUDA(cudaStreamSynchronize(st));  // temporaries are released on return
     return VB200_OK;
 }
 
 static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *init_T, int P) {
-    cudaStream_t st = b->scene->stream;
+    cudaStream_t st = b->stream;
     batch_free_problems(b);
     b->P = P;
     b->iter_base = 0;
@@ -1032,7 +1054,7 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
 // `sp` given, part B also finishes the iteration (reduction + estimator step by each problem's last warp).
 static void launch_pass(Batch *b, bool plane, const PassParams &pp, const SolveParams *sp = nullptr, int pass_index = 0) {
     Scene *sc = b->scene;
-    cudaStream_t st = sc->stream;
+    cudaStream_t st = b->stream;
     SolveParams s0;
     memset(&s0, 0, sizeof(s0));
     const SolveParams &s = sp ? *sp : s0;
@@ -1053,10 +1075,12 @@ static void launch_pass(Batch *b, bool plane, const PassParams &pp, const SolveP
     b->launches += 2;
 }
 
+// Iterations [it_begin, it_end] of the loop (the whole loop is 0..max_iter): vb200_icp_run enqueues the first few
+// of one half of its clouds, uploads the other half meanwhile, then comes back for the rest.
 static int batch_run(Batch *b, int estimator, const double *gravity, double max_dist, double rel_fitness,
-                     double rel_rmse, int max_iter) {
+                     double rel_rmse, int max_iter, int it_begin = 0, int it_end = 0x7fffffff) {
     Scene *sc = b->scene;
-    cudaStream_t st = sc->stream;
+    cudaStream_t st = b->stream;
     if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY || max_iter < 0) return VB200_ERR_INVALID;
     if (!(max_dist > 0.0)) return VB200_ERR_DISTANCE;
     if (max_dist > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
@@ -1081,7 +1105,7 @@ static int batch_run(Batch *b, int estimator, const double *gravity, double max_
     // passes that would only find every problem done.
     const bool can_stop = rel_fitness > 0.0 && rel_rmse > 0.0;
     if (can_stop) sp.ndone = b->d_ndone;
-    for (int it = 0; it <= max_iter; it++) {
+    for (int it = it_begin; it <= std::min(max_iter, it_end); it++) {
         if (can_stop && it >= 4 && (it & 3) == 0) {
             int ndone = 0;
             VB_CUDA(cudaMemcpyAsync(&ndone, b->d_ndone, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1121,8 +1145,7 @@ static int make_params(Batch *b, int estimator, const double *gravity, double ma
 
 // first half of an iteration: correspondence pass + per-problem totals left on the device
 static int batch_pass(Batch *b, int estimator, double max_dist) {
-    Scene *sc = b->scene;
-    cudaStream_t st = sc->stream;
+    cudaStream_t st = b->stream;
     PassParams pp;
     SolveParams sp;
     sp.ndone = nullptr;
@@ -1145,8 +1168,7 @@ static int batch_pass(Batch *b, int estimator, double max_dist) {
 // second half: finish the iteration from the (all-reduced) totals
 static int batch_solve(Batch *b, int estimator, const double *gravity, double max_dist, double rel_fitness,
                        double rel_rmse, int max_iter, int pass_index, const int64_t *npts_global) {
-    Scene *sc = b->scene;
-    cudaStream_t st = sc->stream;
+    cudaStream_t st = b->stream;
     PassParams pp;
     SolveParams sp;
     sp.ndone = nullptr;
@@ -1171,7 +1193,7 @@ static int batch_solve(Batch *b, int estimator, const double *gravity, double ma
 // n unconditional iterations from the current transforms (no convergence test, `done` never set)
 static int batch_iterate(Batch *b, int estimator, const double *gravity, double max_dist, int n_iter) {
     Scene *sc = b->scene;
-    cudaStream_t st = sc->stream;
+    cudaStream_t st = b->stream;
     if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY || n_iter < 0) return VB200_ERR_INVALID;
     if (!(max_dist > 0.0)) return VB200_ERR_DISTANCE;
     if (max_dist > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
@@ -1209,6 +1231,19 @@ static int batch_iterate(Batch *b, int estimator, const double *gravity, double 
     b->ev_valid = timed;
     VB_CUDA(cudaGetLastError());
     return VB200_OK;
+}
+
+constexpr int64_t kPipelineMinPoints = 200000;  // below this a second stream costs more than the copy it hides
+
+// the scene's second stream, created on first use
+static bool second_stream(Scene *sc) {
+    if (sc->stream2) return true;
+    if (cudaStreamCreateWithFlags(&sc->stream2, cudaStreamNonBlocking) != cudaSuccess) {
+        (void)cudaGetLastError();
+        sc->stream2 = nullptr;
+        return false;
+    }
+    return true;
 }
 
 }  // namespace vb
@@ -1268,8 +1303,16 @@ extern "C" int vb200_batch_last_kernel_ms(vb200_batch_t *batch, float *pass_ms, 
     return VB200_OK;
 }
 
+static int batch_create_on(vb200_scene_t *scene, cudaStream_t stream, const double *src_xyz, const double *src_nrm,
+                           const int64_t *src_offsets, int32_t n_clouds, vb200_batch_t **out);
+
 extern "C" int vb200_batch_create(vb200_scene_t *scene, const double *src_xyz, const double *src_nrm,
                                   const int64_t *src_offsets, int32_t n_clouds, vb200_batch_t **out) {
+    return batch_create_on(scene, nullptr, src_xyz, src_nrm, src_offsets, n_clouds, out);
+}
+
+static int batch_create_on(vb200_scene_t *scene, cudaStream_t stream, const double *src_xyz, const double *src_nrm,
+                           const int64_t *src_offsets, int32_t n_clouds, vb200_batch_t **out) {
     if (!out) return VB200_ERR_INVALID;
     *out = nullptr;
     if (!scene || !src_offsets || n_clouds < 0 || (!src_xyz && src_offsets[n_clouds] > src_offsets[0]))
@@ -1278,6 +1321,7 @@ extern "C" int vb200_batch_create(vb200_scene_t *scene, const double *src_xyz, c
     VB_CUDA(cudaSetDevice(sc->device));
     Batch *b = new Batch();
     b->scene = sc;
+    b->stream = stream ? stream : sc->stream;
     b->has_normals = src_nrm != nullptr;  // only presence matters (Registration.cpp:152-157)
     int rc = vb::batch_upload(b, src_xyz, src_offsets, n_clouds);
     if (rc != VB200_OK) {
@@ -1292,7 +1336,7 @@ extern "C" int vb200_batch_destroy(vb200_batch_t *batch) {
     if (!batch) return VB200_OK;
     Batch *b = reinterpret_cast<Batch *>(batch);
     cudaSetDevice(b->scene->device);
-    cudaStreamSynchronize(b->scene->stream);
+    cudaStreamSynchronize(b->stream);
     vb::batch_free(b);
     return VB200_OK;
 }
@@ -1321,8 +1365,8 @@ extern "C" int vb200_batch_results(vb200_batch_t *batch, double *out_T, double *
     std::vector<vb::ProbState> states((size_t)b->P);
     if (b->P)
         VB_CUDA(cudaMemcpyAsync(states.data(), b->d_states, sizeof(vb::ProbState) * (size_t)b->P,
-                                cudaMemcpyDeviceToHost, b->scene->stream));
-    VB_CUDA(cudaStreamSynchronize(b->scene->stream));
+                                cudaMemcpyDeviceToHost, b->stream));
+    VB_CUDA(cudaStreamSynchronize(b->stream));
     for (int p = 0; p < b->P; p++) {
         const vb::ProbState &s = states[p];
         if (out_T) memcpy(out_T + 16 * (size_t)p, s.T, sizeof(double) * 16);
@@ -1341,18 +1385,18 @@ extern "C" int vb200_batch_corr(vb200_batch_t *batch, int32_t p, int32_t *out_co
     VB_CUDA(cudaSetDevice(b->scene->device));
     const vb::ProbDesc &pd = b->probs[p];
     std::vector<int> cj((size_t)pd.npts), so((size_t)pd.npts);
-    vb::DevBuf<int> d_j(b->scene->stream);
+    vb::DevBuf<int> d_j(b->stream);
     if (pd.npts) {
         VB_CUDA(d_j.alloc((size_t)pd.npts));
-        vb::k_corr_orig<<<vb::div_up(pd.npts, 256), 256, 0, b->scene->stream>>>(b->d_corr + pd.corr_begin, pd.npts,
+        vb::k_corr_orig<<<vb::div_up(pd.npts, 256), 256, 0, b->stream>>>(b->d_corr + pd.corr_begin, pd.npts,
                                                                                b->scene->grid.orig, d_j.p);
         VB_CUDA(cudaGetLastError());
         VB_CUDA(cudaMemcpyAsync(cj.data(), d_j.p, sizeof(int) * (size_t)pd.npts,
-                                cudaMemcpyDeviceToHost, b->scene->stream));
+                                cudaMemcpyDeviceToHost, b->stream));
         VB_CUDA(cudaMemcpyAsync(so.data(), b->d_src_orig + pd.src_begin, sizeof(int) * (size_t)pd.npts,
-                                cudaMemcpyDeviceToHost, b->scene->stream));
+                                cudaMemcpyDeviceToHost, b->stream));
     }
-    VB_CUDA(cudaStreamSynchronize(b->scene->stream));
+    VB_CUDA(cudaStreamSynchronize(b->stream));
     // sorted position -> original source index, then emit in ascending source index
     std::vector<int> by_src((size_t)pd.npts, -1);
     for (int s = 0; s < pd.npts; s++) by_src[(size_t)so[s]] = cj[s];
@@ -1390,19 +1434,46 @@ extern "C" int vb200_icp_run(vb200_scene_t *scene, const double *src_xyz, const 
     Scene *sc = reinterpret_cast<Scene *>(scene);
     if (!(max_dist > 0.0)) { passthrough(); return VB200_ERR_DISTANCE; }
     if (estimator != VB200_EST_P2P && (!src_nrm || !sc->has_normals)) { passthrough(); return VB200_ERR_NORMALS; }
-    vb200_batch_t *batch = nullptr;
-    int rc = vb200_batch_create(scene, src_xyz, src_nrm, src_offsets, B, &batch);
-    if (rc != VB200_OK) return rc;
-    rc = vb200_batch_set_problems(batch, nullptr, init_T, B);
-    if (rc == VB200_OK) rc = vb200_batch_run(batch, estimator, gravity_axis, max_dist, rel_fitness, rel_rmse, max_iter);
-    if (rc == VB200_OK) rc = vb200_batch_results(batch, out_T, out_fitness, out_rmse, out_ncorr, out_iters);
-    if (rc == VB200_OK && out_corr) {
-        for (int p = 0; p < B && rc == VB200_OK; p++) {
-            int32_t k = 0;
-            rc = vb200_batch_corr(batch, p, out_corr + 2 * (src_offsets[p] - src_offsets[0]), &k);
+    // Two halves on two streams when there is enough to move: the second half's host-to-device copy and
+    // spatial sort run while the first half's opening iterations compute (the objects are independent, so
+    // nothing else changes).  38 MB of sources are ~0.8 ms of PCIe time, half of which this hides.
+    VB_CUDA(cudaSetDevice(sc->device));
+    const int64_t total = src_offsets[B] - src_offsets[0];
+    int split = B;  // clouds [0, split) on the scene's stream, [split, B) on its second one
+    if (B >= 2 && total >= vb::kPipelineMinPoints && max_iter >= 4 && vb::second_stream(sc)) {
+        split = 1;
+        while (split < B - 1 && 2 * (src_offsets[split] - src_offsets[0]) < total) split++;
+    }
+    vb200_batch_t *half[2] = {nullptr, nullptr};
+    const int first[3] = {0, split, B};
+    const int nhalf = split < B ? 2 : 1;
+    const int warm = 3;  // iterations 0..3 of the first half are enqueued before the second half is uploaded
+    int rc = VB200_OK;
+    for (int h = 0; h < nhalf && rc == VB200_OK; h++) {
+        const int p0 = first[h], np = first[h + 1] - first[h];
+        rc = batch_create_on(scene, h == 0 ? nullptr : sc->stream2, src_xyz, src_nrm, src_offsets + p0, np, &half[h]);
+        if (rc == VB200_OK) rc = vb200_batch_set_problems(half[h], nullptr, init_T + 16 * (size_t)p0, np);
+        if (rc == VB200_OK)
+            rc = vb::batch_run(reinterpret_cast<Batch *>(half[h]), estimator, gravity_axis, max_dist, rel_fitness,
+                               rel_rmse, max_iter, 0, nhalf == 2 ? warm : 0x7fffffff);
+    }
+    for (int h = 0; h < nhalf && rc == VB200_OK && nhalf == 2; h++)
+        rc = vb::batch_run(reinterpret_cast<Batch *>(half[h]), estimator, gravity_axis, max_dist, rel_fitness, rel_rmse,
+                           max_iter, warm + 1);
+    for (int h = 0; h < nhalf && rc == VB200_OK; h++) {
+        const int p0 = first[h], np = first[h + 1] - first[h];
+        rc = vb200_batch_results(half[h], out_T ? out_T + 16 * (size_t)p0 : nullptr, out_fitness ? out_fitness + p0 : nullptr,
+                                 out_rmse ? out_rmse + p0 : nullptr, out_ncorr ? out_ncorr + p0 : nullptr,
+                                 out_iters ? out_iters + p0 : nullptr);
+        if (rc == VB200_OK && out_corr) {
+            for (int p = 0; p < np && rc == VB200_OK; p++) {
+                int32_t k = 0;
+                rc = vb200_batch_corr(half[h], p, out_corr + 2 * (src_offsets[p0 + p] - src_offsets[0]), &k);
+            }
         }
     }
-    vb200_batch_destroy(batch);
+    for (int h = 0; h < 2; h++)
+        if (half[h]) vb200_batch_destroy(half[h]);
     return rc;
 }
 

@@ -290,6 +290,7 @@ void scene_free(Scene *sc) {
     cudaFree((void *)sc->grid.xyz);
     cudaFree((void *)sc->grid.nrm);
     cudaFree((void *)sc->grid.orig);
+    if (sc->stream2) cudaStreamDestroy(sc->stream2);
     if (sc->stream) cudaStreamDestroy(sc->stream);
     delete sc;
 }

@@ -8,6 +8,7 @@ namespace vb {
 struct Scene {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // created on first use by vb200_icp_run (second half of a pipelined batch)
     GridDev grid{};
     int64_t n = 0;
     int64_t ncoarse = 0;
