@@ -77,6 +77,17 @@ int vb200_knn1(vb200_scene_t *scene, const double *q_xyz, int64_t Q, double radi
  * d_q_xyz Q x 3 doubles, d_out_idx Q int32, d_out_d2 Q doubles. */
 int vb200_knn1_device(vb200_scene_t *scene, const void *d_q_xyz, int64_t Q, double radius,
                       void *d_out_idx, void *d_out_d2);
+/* The same operator by exhaustive search, without a scene handle: every (query, target) distance in the
+ * reference's double arithmetic (flann::L2, O3D/3rdparty/flann/algorithms/dist.h:150-177), the target cloud
+ * streamed through shared memory by the TMA engine.  Same outputs bit for bit as vb200_knn1 (same threshold
+ * rule, ties to the lowest target index).  Meant for a handful of queries against a cloud nothing has indexed
+ * yet (it streams 24 B per target point once per 8 queries and is FP64-bound beyond that) and as the
+ * independent on-device check of the grid search.  Limits: Q <= 524 280 per call; the device variant needs a
+ * 16-byte aligned target pointer and runs asynchronously on `cuda_stream` (a cudaStream_t, NULL = default). */
+int vb200_knn1_bruteforce(const double *tgt_xyz, int64_t n, const double *q_xyz, int64_t Q, double radius,
+                          int device, int32_t *out_idx, double *out_d2);
+int vb200_knn1_bruteforce_device(const void *d_tgt_xyz, int64_t n, const void *d_q_xyz, int64_t Q, double radius,
+                                 int device, void *d_out_idx, void *d_out_d2, void *cuda_stream);
 
 /* ---- ICP operator: replaces open3d::RegistrationICP (O3D/src/Core/Registration/Registration.h:102-107,
  * Registration.cpp:141-186) for a BATCH of B independent sources against one scene.

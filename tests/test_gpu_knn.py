@@ -125,3 +125,40 @@ def test_large_coherent_batch_path(vb, oracle, scene):
     gi, gd = sc.SearchHybrid1(q, 0.075)
     oi, od = oracle.Index(tgt, 0.075).knn1(q, 0.075)
     assert (gi == oi).all() and (gd == od).all()
+
+
+def test_bruteforce_matches_oracle_bitexact(vb, oracle):
+    """vb200_knn1_bruteforce (TMA-staged exhaustive search) against the oracle: ragged tile / chunk sizes,
+    targets smaller than one tile, none at all, ties."""
+    rng = np.random.default_rng(7)
+    for n, nq in ((5000, 301), (1024, 8), (1023, 7), (3 * 1024 + 1, 64), (17, 5), (9000, 1)):
+        tgt = rng.uniform(0, 1, (n, 3))
+        q = np.concatenate([tgt[: nq // 2] + rng.normal(0, 0.01, (nq // 2, 3)), rng.uniform(-1, 2, (nq - nq // 2, 3))])
+        gi, gd = vb.reg.SearchHybrid1BruteForce(tgt, q, 0.075)
+        oi, od = oracle.Index(tgt, 0.075).knn1(q, 0.075)
+        assert (gi == oi).all() and (gd == od).all(), (n, nq)
+    # duplicates: exact ties go to the lowest target index; empty target; empty query set
+    tgt = np.array([[0, 0, 0.0], [0, 0, 0.0], [1.0, 0, 0], [1.02, 0, 0], [1.0, 0, 0], [5, 5, 5]])
+    q = np.array([[1.01, 0, 0], [1.0, 0, 0], [0, 0, 0.0], [3, 3, 3.0]])
+    gi, gd = vb.reg.SearchHybrid1BruteForce(tgt, q, 0.075)
+    assert list(gi) == [2, 2, 0, -1] and gd[3] == 0.0
+    gi, gd = vb.reg.SearchHybrid1BruteForce(np.zeros((0, 3)), q, 0.075)
+    assert (gi == -1).all() and (gd == 0).all()
+    gi, gd = vb.reg.SearchHybrid1BruteForce(tgt, np.zeros((0, 3)), 0.075)
+    assert len(gi) == 0
+    with pytest.raises(vb.pkg.VismaB200Error):
+        vb.reg.SearchHybrid1BruteForce(tgt, q, 0.0)
+
+
+def test_grid_search_equals_exhaustive_search_at_full_size(vb):
+    """BASELINE size: the grid search and the index-free exhaustive search are two independent implementations of
+    the same operator; on the 2 M-point scene they must agree bit for bit (indices and double distances) —
+    2e10 distance evaluations no CPU oracle finishes in a test."""
+    d = vb.synth.make_room_scene(2_000_000, 8, 100)
+    tgt = d["scene_xyz"]
+    q = np.concatenate([vb.synth.knn_queries(tgt, 8000, sigma=0.01), vb.synth.knn_queries(tgt, 2000, sigma=0.08, seed=9)])
+    sc = vb.reg.Scene(tgt, 0.075)
+    gi, gd = sc.SearchHybrid1(q, 0.075)
+    bi, bd = vb.reg.SearchHybrid1BruteForce(tgt, q, 0.075)
+    assert (gi == bi).all() and (gd == bd).all()
+    assert (gi >= 0).sum() > 7000 and (gi < 0).sum() > 300

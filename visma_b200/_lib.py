@@ -18,7 +18,7 @@ EST_P2P, EST_P2PLANE, EST_P2PLANE_GRAVITY = 0, 1, 2
 SYMBOLS = [
     "vb200_version", "vb200_strerror", "vb200_last_error", "vb200_device_count",
     "vb200_scene_create", "vb200_scene_destroy", "vb200_scene_size", "vb200_scene_stream",
-    "vb200_scene_sync", "vb200_knn1", "vb200_knn1_device", "vb200_icp_run", "vb200_batch_create",
+    "vb200_scene_sync", "vb200_knn1", "vb200_knn1_device", "vb200_knn1_bruteforce", "vb200_knn1_bruteforce_device", "vb200_icp_run", "vb200_batch_create",
     "vb200_batch_destroy", "vb200_batch_set_problems", "vb200_batch_run", "vb200_batch_results",
     "vb200_batch_corr", "vb200_batch_launches", "vb200_batch_iterate", "vb200_batch_last_kernel_ms", "vb200_batch_pass",
     "vb200_batch_set_totals_buffer", "vb200_batch_totals", "vb200_batch_solve", "vb200_estimate", "vb200_register_model_to_scene",
@@ -68,6 +68,8 @@ def lib():
     L.vb200_scene_sync.argtypes = [vp]
     L.vb200_knn1.argtypes = [vp, dp, C.c_int64, C.c_double, ip, dp]
     L.vb200_knn1_device.argtypes = [vp, vp, C.c_int64, C.c_double, vp, vp]
+    L.vb200_knn1_bruteforce.argtypes = [dp, C.c_int64, dp, C.c_int64, C.c_double, C.c_int, ip, dp]
+    L.vb200_knn1_bruteforce_device.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_double, C.c_int, vp, vp, vp]
     L.vb200_icp_run.argtypes = [vp, dp, dp, i64p, C.c_int32, dp, C.c_int, dp, C.c_double, C.c_double,
                                 C.c_double, C.c_int, dp, dp, dp, ip, ip, ip]
     L.vb200_batch_create.argtypes = [vp, dp, dp, i64p, C.c_int32, C.POINTER(vp)]

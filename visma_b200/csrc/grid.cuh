@@ -77,6 +77,14 @@ __device__ __forceinline__ double l2_exact(double qx, double qy, double qz, cons
     return r;
 }
 
+__device__ __forceinline__ double l2_exact(double qx, double qy, double qz, double tx, double ty, double tz) {
+    double dx = __dsub_rn(qx, tx), dy = __dsub_rn(qy, ty), dz = __dsub_rn(qz, tz);
+    double r = __dmul_rn(dx, dx);
+    r = __dadd_rn(r, __dmul_rn(dy, dy));
+    r = __dadd_rn(r, __dmul_rn(dz, dz));
+    return r;
+}
+
 struct QueryCtx {
     float qx, qy, qz;  // centred f32 query
     float fx, fy, fz;  // position inside the home fine cell, in fine-cell units [0,1)

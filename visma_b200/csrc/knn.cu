@@ -5,6 +5,8 @@
 // arithmetic: same neighbour index, same d2 (see grid.cuh).
 #include <math.h>
 
+#include <algorithm>
+
 #include "scene.cuh"
 
 namespace vb {
@@ -50,6 +52,171 @@ __global__ void __launch_bounds__(kTpb) k_knn1_wpq(GridDev G, const double *__re
         out_idx[i] = bs >= 0 ? __ldg(G.orig + bs) : -1;
         out_d2[i] = bs >= 0 ? d2 : 0.0;
     }
+}
+
+// ---- exhaustive search: vb200_knn1_bruteforce -------------------------------------------------------
+// The same operator without any index: every (query, target) distance in the reference's double arithmetic.
+// It needs no scene handle (nothing to build), streams the target cloud exactly once per chunk of 8 queries,
+// and is the independent on-device check of the grid search at sizes no CPU oracle finishes
+// (tests/test_gpu_knn.py).  With a handful of queries it is the HBM-streaming case SURVEY §8d's algorithmic
+// bytes describe (24 B per target point here: the cloud stays in the caller's f64 layout); beyond ~8 queries
+// it is bound by the FP64 pipe (8 rounded operations per pair, no FMA: FLANN's operation order).
+//
+// grid = (slices of the target cloud, chunks of kBfQ queries).  A block streams its slice through shared
+// memory in tiles of kBfTile points moved by the TMA engine (cp.async.bulk + mbarrier, kBfStages tiles in
+// flight, issued by one thread); thread i takes points i, i + 128, ... of a tile against the chunk's queries
+// held in registers; at the end the block's per-query (d2, index) minima are combined with warp shuffles and
+// one shared-memory step, and k_bf_merge combines the slices.  Ties: lowest target index, as everywhere.
+constexpr int kBfTpb = 128, kBfQ = 8, kBfTile = 1024, kBfStages = 3;
+constexpr int kBfTileBytes = kBfTile * 24;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// one elected thread: arm the barrier with the byte count, then let the TMA engine copy global -> shared
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ bool bf_less(double d, int i, double bd, int bi) { return d < bd || (d == bd && i < bi); }
+
+__global__ void __launch_bounds__(kBfTpb) k_bf_knn1(const double *__restrict__ tgt, int64_t n, int64_t slice_pts,
+                                                    const double *__restrict__ q, int64_t nq,
+                                                    double *__restrict__ part_d2, int *__restrict__ part_idx) {
+    extern __shared__ __align__(128) unsigned char bf_smem[];
+    double *tiles = reinterpret_cast<double *>(bf_smem);  // kBfStages x kBfTile x 3 doubles
+    __shared__ __align__(8) unsigned long long bars[kBfStages];
+    __shared__ double red_d[kBfTpb / 32][kBfQ];
+    __shared__ int red_i[kBfTpb / 32][kBfQ];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t p_begin = (int64_t)blockIdx.x * slice_pts;
+    const int64_t p_end = min(n, p_begin + slice_pts);
+    const int64_t q0 = (int64_t)blockIdx.y * kBfQ;
+    // the chunk's queries: warp-uniform loads, kept in registers (a missing query repeats the last one)
+    double qx[kBfQ], qy[kBfQ], qz[kBfQ], bd[kBfQ];
+    int bi[kBfQ];
+#pragma unroll
+    for (int j = 0; j < kBfQ; j++) {
+        const int64_t qi = min(q0 + j, nq - 1);
+        qx[j] = q[3 * qi]; qy[j] = q[3 * qi + 1]; qz[j] = q[3 * qi + 2];
+        bd[j] = 1.0e300; bi[j] = 0x7fffffff;
+    }
+    const int64_t npts = p_end - p_begin;
+    const int nfull = (int)(npts / kBfTile);  // whole tiles go through the TMA engine, the ragged tail through plain loads
+    if (tid == 0) {
+        for (int s2 = 0; s2 < kBfStages; s2++) mbar_init(smem_u32(&bars[s2]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int t = 0; t < kBfStages && t < nfull; t++)
+            tma_load_1d(smem_u32(tiles + (size_t)t * kBfTile * 3), tgt + 3 * (p_begin + (int64_t)t * kBfTile), kBfTileBytes,
+                        smem_u32(&bars[t]));
+    }
+    for (int t = 0; t < nfull; t++) {
+        const int st = t % kBfStages;
+        mbar_wait(smem_u32(&bars[st]), (unsigned)((t / kBfStages) & 1));
+        const double *tile = tiles + (size_t)st * kBfTile * 3;
+        const int base = (int)(p_begin + (int64_t)t * kBfTile);
+#pragma unroll 2
+        for (int i = tid; i < kBfTile; i += kBfTpb) {
+            const double tx = tile[3 * i], ty = tile[3 * i + 1], tz = tile[3 * i + 2];
+#pragma unroll
+            for (int j = 0; j < kBfQ; j++) {
+                const double d = l2_exact(qx[j], qy[j], qz[j], tx, ty, tz);
+                if (bf_less(d, base + i, bd[j], bi[j])) { bd[j] = d; bi[j] = base + i; }
+            }
+        }
+        __syncthreads();  // every thread is done with this stage: it can be refilled
+        if (tid == 0 && t + kBfStages < nfull)
+            tma_load_1d(smem_u32(tiles + (size_t)st * kBfTile * 3),
+                        tgt + 3 * (p_begin + (int64_t)(t + kBfStages) * kBfTile), kBfTileBytes, smem_u32(&bars[st]));
+    }
+    for (int64_t i = p_begin + (int64_t)nfull * kBfTile + tid; i < p_end; i += kBfTpb) {
+        const double tx = tgt[3 * i], ty = tgt[3 * i + 1], tz = tgt[3 * i + 2];
+#pragma unroll
+        for (int j = 0; j < kBfQ; j++) {
+            const double d = l2_exact(qx[j], qy[j], qz[j], tx, ty, tz);
+            if (bf_less(d, (int)i, bd[j], bi[j])) { bd[j] = d; bi[j] = (int)i; }
+        }
+    }
+    // per-query minimum over the block: butterflies inside each warp, then one step through shared memory
+#pragma unroll
+    for (int j = 0; j < kBfQ; j++) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd[j], o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi[j], o);
+            if (bf_less(od, oi, bd[j], bi[j])) { bd[j] = od; bi[j] = oi; }
+        }
+        if (lane == 0) { red_d[warp][j] = bd[j]; red_i[warp][j] = bi[j]; }
+    }
+    __syncthreads();
+    if (tid < kBfQ && q0 + tid < nq) {
+        double d = red_d[0][tid];
+        int i = red_i[0][tid];
+        for (int w = 1; w < kBfTpb / 32; w++)
+            if (bf_less(red_d[w][tid], red_i[w][tid], d, i)) { d = red_d[w][tid]; i = red_i[w][tid]; }
+        part_d2[(int64_t)blockIdx.x * nq + q0 + tid] = d;
+        part_idx[(int64_t)blockIdx.x * nq + q0 + tid] = i;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bf_merge(const double *__restrict__ part_d2, const int *__restrict__ part_idx,
+                                                  int nslices, int64_t nq, double r2, int *__restrict__ out_idx,
+                                                  double *__restrict__ out_d2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    double d = part_d2[i];
+    int b = part_idx[i];
+    for (int s2 = 1; s2 < nslices; s2++) {
+        const double od = part_d2[(int64_t)s2 * nq + i];
+        const int oi = part_idx[(int64_t)s2 * nq + i];
+        if (bf_less(od, oi, d, b)) { d = od; b = oi; }
+    }
+    const bool hit = b != 0x7fffffff && d < r2;  // accepted iff d2 < (double)(float)(r*r) (KDTreeFlann.cpp:185)
+    out_idx[i] = hit ? b : -1;
+    out_d2[i] = hit ? d : 0.0;
+}
+
+int bf_launch(const double *d_tgt, int64_t n, const double *d_q, int64_t nq, double radius, int *d_idx, double *d_d2,
+              cudaStream_t st) {
+    if (!(radius > 0.0) || n < 0 || nq < 0 || n > 0x7ffffffe || nq > 0x7fffffff) return VB200_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_tgt) & 15) != 0) return VB200_ERR_INVALID;  // the bulk copies need 16-byte alignment
+    if (nq == 0) return VB200_OK;
+    const double r2 = (double)(float)(radius * radius);
+    const int nchunks = div_up(nq, kBfQ);
+    if (nchunks > 65535) return VB200_ERR_INVALID;  // grid.y; 524 280 queries per call
+    // enough blocks for two waves when there are few queries; slices are whole tiles so every bulk copy starts
+    // on a 16-byte boundary (1024 points x 24 B)
+    int64_t nslices = std::max<int64_t>(1, std::min<int64_t>(div_up(2 * kNumSMsB200, nchunks), div_up(std::max<int64_t>(n, 1), 4 * kBfTile)));
+    int64_t slice_pts = div_up(div_up(std::max<int64_t>(n, 1), nslices), kBfTile) * (int64_t)kBfTile;
+    nslices = std::max<int64_t>(1, div_up(std::max<int64_t>(n, 1), slice_pts));
+    DevBuf<double> p_d2(st);
+    DevBuf<int> p_idx(st);
+    VB_CUDA(p_d2.alloc((size_t)nslices * (size_t)nq));
+    VB_CUDA(p_idx.alloc((size_t)nslices * (size_t)nq));
+    const size_t smem = (size_t)kBfStages * kBfTileBytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VB_CUDA(cudaFuncSetAttribute(k_bf_knn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_bf_knn1<<<dim3((unsigned)nslices, (unsigned)nchunks), kBfTpb, smem, st>>>(d_tgt, n, slice_pts, d_q, nq, p_d2.p, p_idx.p);
+    k_bf_merge<<<div_up(nq, 256), 256, 0, st>>>(p_d2.p, p_idx.p, (int)nslices, nq, r2, d_idx, d_d2);
+    VB_CUDA(cudaGetLastError());
+    return VB200_OK;
 }
 
 constexpr int64_t kWarpPerQueryMax = 262144;  // below this many queries a warp per query fills the GPU better
@@ -105,5 +272,38 @@ extern "C" int vb200_knn1(vb200_scene_t *scene, const double *q_xyz, int64_t Q, 
     VB_CUDA(cudaMemcpyAsync(out_idx, d_idx.p, sizeof(int) * (size_t)Q, cudaMemcpyDeviceToHost, sc->stream));
     VB_CUDA(cudaMemcpyAsync(out_d2, d_d2.p, sizeof(double) * (size_t)Q, cudaMemcpyDeviceToHost, sc->stream));
     VB_CUDA(cudaStreamSynchronize(sc->stream));
+    return VB200_OK;
+}
+
+extern "C" int vb200_knn1_bruteforce_device(const void *d_tgt_xyz, int64_t n, const void *d_q_xyz, int64_t Q,
+                                            double radius, int device, void *d_out_idx, void *d_out_d2,
+                                            void *cuda_stream) {
+    if (n < 0 || Q < 0 || (n > 0 && !d_tgt_xyz) || (Q > 0 && (!d_q_xyz || !d_out_idx || !d_out_d2))) return VB200_ERR_INVALID;
+    VB_TRY(vb::select_device(device));
+    return vb::bf_launch((const double *)d_tgt_xyz, n, (const double *)d_q_xyz, Q, radius, (int *)d_out_idx,
+                         (double *)d_out_d2, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int vb200_knn1_bruteforce(const double *tgt_xyz, int64_t n, const double *q_xyz, int64_t Q, double radius,
+                                     int device, int32_t *out_idx, double *out_d2) {
+    if (n < 0 || Q < 0 || (n > 0 && !tgt_xyz) || (Q > 0 && (!q_xyz || !out_idx || !out_d2))) return VB200_ERR_INVALID;
+    if (!(radius > 0.0)) return VB200_ERR_INVALID;
+    VB_TRY(vb::select_device(device));
+    if (Q == 0) return VB200_OK;
+    cudaStream_t st;
+    VB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
+    vb::DevBuf<double> d_t(st), d_q(st), d_d2(st);
+    vb::DevBuf<int> d_idx(st);
+    VB_CUDA(d_t.alloc(3 * (size_t)std::max<int64_t>(n, 1)));
+    VB_CUDA(d_q.alloc(3 * (size_t)Q));
+    VB_CUDA(d_d2.alloc((size_t)Q));
+    VB_CUDA(d_idx.alloc((size_t)Q));
+    if (n) VB_CUDA(cudaMemcpyAsync(d_t.p, tgt_xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMemcpyAsync(d_q.p, q_xyz, sizeof(double) * 3 * (size_t)Q, cudaMemcpyHostToDevice, st));
+    VB_TRY(vb::bf_launch(d_t.p, n, d_q.p, Q, radius, d_idx.p, d_d2.p, st));
+    VB_CUDA(cudaMemcpyAsync(out_idx, d_idx.p, sizeof(int) * (size_t)Q, cudaMemcpyDeviceToHost, st));
+    VB_CUDA(cudaMemcpyAsync(out_d2, d_d2.p, sizeof(double) * (size_t)Q, cudaMemcpyDeviceToHost, st));
+    VB_CUDA(cudaStreamSynchronize(st));
     return VB200_OK;
 }

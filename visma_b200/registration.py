@@ -135,6 +135,18 @@ class Scene:
         return idx, d2
 
 
+def SearchHybrid1BruteForce(target, queries, radius, device=0):
+    """KDTreeFlann::SearchHybrid(q, radius, 1) by exhaustive search (vb200_knn1_bruteforce): no index is
+    built; every distance is taken in the reference's double arithmetic.  Same outputs as
+    Scene.SearchHybrid1, bit for bit."""
+    t, q = _f64(target), _f64(queries)
+    idx = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q), np.float64)
+    check(lib().vb200_knn1_bruteforce(_dp(t), len(t), _dp(q), len(q), float(radius), int(device), _ip(idx), _dp(d2)),
+          "vb200_knn1_bruteforce")
+    return idx, d2
+
+
 class Batch:
     """Resident source clouds + ICP problems (cloud id, init) on a Scene."""
 
