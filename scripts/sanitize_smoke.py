@@ -20,6 +20,10 @@ print("iterate", [round(x.fitness_, 4) for x in b.results()])
 b.close()
 i, d2 = sc.SearchHybrid1(synth.knn_queries(d["scene_xyz"], 3000), 0.075)
 print("knn matched", int((i >= 0).sum()))
+bi, bd2 = reg.SearchHybrid1BruteForce(d["scene_xyz"], synth.knn_queries(d["scene_xyz"], 3000), 0.075)
+print("exhaustive knn equals grid", bool((bi == i).all() and (bd2 == d2).all()))
+for nq in (1, 2, 3):
+    reg.SearchHybrid1BruteForce(d["scene_xyz"], d["scene_xyz"][:nq] + 0.001, 0.075)
 print("register", reg.RegisterModelToScene(cl[0], sc, 4, 0.05, True)["ncorr"])
 print("estimate", reg.ComputeTransformation(reg.TransformationEstimationPointToPlane(), cl[0].points_,
                                             reg.PointCloud(d["scene_xyz"], d["scene_nrm"]),
@@ -32,3 +36,6 @@ ren.SetCamera(0.05, 10.0, 100.0, 100.0, 80.0, 60.0)
 ren.SetMesh(V, F)
 m = synth.make_T(np.eye(3), [0, 0, 0.6])
 print("render", int((ren.RenderDepth(m) < 1).sum()), int(ren.RenderEdge(m).max()), int(ren.RenderMask(m).max()))
+Vc, Fc = synth.cube_mesh()
+ren.SetMesh(Vc, Fc)  # straddles the near plane and fills the image: clipped polygons + the queued big triangles
+print("render cube", int((ren.RenderDepth(synth.make_T(synth.rot_xyz(0.3, 0.5, -0.2), [0, 0, 0.3])) < 1).sum()))

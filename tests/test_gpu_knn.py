@@ -131,7 +131,7 @@ def test_bruteforce_matches_oracle_bitexact(vb, oracle):
     """vb200_knn1_bruteforce (TMA-staged exhaustive search) against the oracle: ragged tile / chunk sizes,
     targets smaller than one tile, none at all, ties."""
     rng = np.random.default_rng(7)
-    for n, nq in ((5000, 301), (1024, 8), (1023, 7), (3 * 1024 + 1, 64), (17, 5), (9000, 1)):
+    for n, nq in ((5000, 301), (1024, 8), (1023, 7), (3 * 1024 + 1, 64), (17, 5), (9000, 1), (2500, 2), (2500, 3), (4100, 4)):
         tgt = rng.uniform(0, 1, (n, 3))
         q = np.concatenate([tgt[: nq // 2] + rng.normal(0, 0.01, (nq // 2, 3)), rng.uniform(-1, 2, (nq - nq // 2, 3))])
         gi, gd = vb.reg.SearchHybrid1BruteForce(tgt, q, 0.075)
@@ -162,3 +162,20 @@ def test_grid_search_equals_exhaustive_search_at_full_size(vb):
     bi, bd = vb.reg.SearchHybrid1BruteForce(tgt, q, 0.075)
     assert (gi == bi).all() and (gd == bd).all()
     assert (gi >= 0).sum() > 7000 and (gi < 0).sum() > 300
+
+
+def test_nan_points_are_never_neighbours(vb, oracle):
+    """A NaN target or query point matches nothing (the reference's `dist < worst_dist` is false for NaN), in the
+    grid search and in the exhaustive one, whatever the NaN's sign bit."""
+    rng = np.random.default_rng(11)
+    tgt = rng.uniform(0, 1, (3000, 3))
+    tgt[5] = np.nan
+    tgt[700, 1] = -np.nan
+    tgt[1500, 2] = np.copysign(np.nan, -1.0)
+    q = np.concatenate([tgt[:1000] + 0.001, [[np.nan, 0.5, 0.5], [0.5, np.copysign(np.nan, -1.0), 0.5]]])
+    oi, od = oracle.Index(tgt, 0.075).knn1(q, 0.075)
+    gi, gd = vb.reg.Scene(tgt, 0.075).SearchHybrid1(q, 0.075)
+    bi, bd = vb.reg.SearchHybrid1BruteForce(tgt, q, 0.075)
+    assert (gi == oi).all() and (gd == od).all()
+    assert (bi == oi).all() and (bd == od).all()
+    assert not np.isin(gi, [5, 700, 1500]).any() and gi[-1] == -1 and gi[-2] == -1

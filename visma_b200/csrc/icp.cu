@@ -613,15 +613,14 @@ __device__ __forceinline__ void reduce_partials(const ProbDesc &pd, const double
     // 16 independent loads in flight per thread (the rows sit in L2; the chain of adds keeps its fixed order)
     const double *col = partials + (int64_t)pd.blk_begin * kRowsPerBlock * kPart + e;
     const int nrows = pd.blk_count * kRowsPerBlock;
-    int b = grp;
-    for (; b + 4 * 15 < nrows; b += 4 * 16) {
+    // (the ragged last batch is predicated, not a loop of dependent loads: adding +0.0 leaves the sum's bits alone)
+    for (int b = grp; b < nrows; b += 4 * 16) {
         double v[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = col[(int64_t)(b + 4 * i) * kPart];
+        for (int i = 0; i < 16; i++) v[i] = b + 4 * i < nrows ? col[(int64_t)(b + 4 * i) * kPart] : 0.0;
 #pragma unroll
         for (int i = 0; i < 16; i++) s += v[i];
     }
-    for (; b < nrows; b += 4) s += col[(int64_t)b * kPart];
     sw[grp][e] = s;
     __syncthreads();
     if (threadIdx.x < kPart) sw[0][e] = ((sw[0][e] + sw[1][e]) + sw[2][e]) + sw[3][e];

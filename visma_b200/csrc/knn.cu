@@ -4,6 +4,7 @@
 // O3D/src/Core/Geometry/KDTreeFlann.cpp:165-189).  Results are bit-identical to the reference's double
 // arithmetic: same neighbour index, same d2 (see grid.cuh).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(kTpb) k_knn1(GridDev G, const double *__restri
 
 // one warp per query (few / scattered queries)
 __global__ void __launch_bounds__(kTpb) k_knn1_wpq(GridDev G, const double *__restrict__ q, int64_t nq, double r2,
-                                                   float r2_ub, int *__restrict__ out_idx,
+                                                   float r2_ub, int bfs, int *__restrict__ out_idx,
                                                    double *__restrict__ out_d2) {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= nq) return;  // warp-uniform exit
@@ -47,7 +48,11 @@ __global__ void __launch_bounds__(kTpb) k_knn1_wpq(GridDev G, const double *__re
     QueryCtx c;
     int bs = -1;
     double d2 = 0.0;
-    if (make_query(G.p, x, y, z, c)) bs = nn_search_wpq(G, c, x, y, z, r2, r2_ub, &d2);
+    __shared__ WpqScratch ws[kTpb / 32];
+    if (make_query(G.p, x, y, z, c)) {
+        bs = bfs ? nn_search_wpq_bfs(G, c, x, y, z, r2, r2_ub, ws[threadIdx.x >> 5], &d2)
+                 : nn_search_wpq(G, c, x, y, z, r2, r2_ub, &d2);
+    }
     if ((threadIdx.x & 31) == 0) {
         out_idx[i] = bs >= 0 ? __ldg(G.orig + bs) : -1;
         out_d2[i] = bs >= 0 ? d2 : 0.0;
@@ -62,12 +67,12 @@ __global__ void __launch_bounds__(kTpb) k_knn1_wpq(GridDev G, const double *__re
 // bytes describe (24 B per target point here: the cloud stays in the caller's f64 layout); beyond ~8 queries
 // it is bound by the FP64 pipe (8 rounded operations per pair, no FMA: FLANN's operation order).
 //
-// grid = (slices of the target cloud, chunks of kBfQ queries).  A block streams its slice through shared
+// grid = (slices of the target cloud, chunks of up to 8 queries).  A block streams its slice through shared
 // memory in tiles of kBfTile points moved by the TMA engine (cp.async.bulk + mbarrier, kBfStages tiles in
 // flight, issued by one thread); thread i takes points i, i + 128, ... of a tile against the chunk's queries
 // held in registers; at the end the block's per-query (d2, index) minima are combined with warp shuffles and
 // one shared-memory step, and k_bf_merge combines the slices.  Ties: lowest target index, as everywhere.
-constexpr int kBfTpb = 128, kBfQ = 8, kBfTile = 1024, kBfStages = 3;
+constexpr int kBfTpb = 128, kBfTile = 1024, kBfStages = 3;
 constexpr int kBfTileBytes = kBfTile * 24;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -89,25 +94,35 @@ __device__ __forceinline__ void tma_load_1d(unsigned dst, const void *src, unsig
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__device__ __forceinline__ bool bf_less(double d, int i, double bd, int bi) { return d < bd || (d == bd && i < bi); }
+// (d, i) before (bd, bi): smaller distance, then lower index.  The distances are sums of squares (>= +0.0, or
+// NaN), for which the IEEE bit patterns order like signed integers — the comparison runs on the integer pipe
+// and leaves the FP64 pipe to the 8 operations of the distance itself.  NaN patterns sort above everything
+// (a NaN query or target point is never anyone's neighbour, as in the reference: `dist < worst_dist` is false).
+__device__ __forceinline__ bool bf_less(double d, int i, double bd, int bi) {
+    long long a = __double_as_longlong(d);
+    const long long b = __double_as_longlong(bd);
+    if (a < 0) a = 0x7fffffffffffffffll;  // a NaN with its sign bit set (a sum of squares is never negative)
+    return a < b || (a == b && i < bi);
+}
 
+template <int NQ>
 __global__ void __launch_bounds__(kBfTpb) k_bf_knn1(const double *__restrict__ tgt, int64_t n, int64_t slice_pts,
                                                     const double *__restrict__ q, int64_t nq,
                                                     double *__restrict__ part_d2, int *__restrict__ part_idx) {
     extern __shared__ __align__(128) unsigned char bf_smem[];
     double *tiles = reinterpret_cast<double *>(bf_smem);  // kBfStages x kBfTile x 3 doubles
     __shared__ __align__(8) unsigned long long bars[kBfStages];
-    __shared__ double red_d[kBfTpb / 32][kBfQ];
-    __shared__ int red_i[kBfTpb / 32][kBfQ];
+    __shared__ double red_d[kBfTpb / 32][NQ];
+    __shared__ int red_i[kBfTpb / 32][NQ];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p_begin = (int64_t)blockIdx.x * slice_pts;
     const int64_t p_end = min(n, p_begin + slice_pts);
-    const int64_t q0 = (int64_t)blockIdx.y * kBfQ;
+    const int64_t q0 = (int64_t)blockIdx.y * NQ;
     // the chunk's queries: warp-uniform loads, kept in registers (a missing query repeats the last one)
-    double qx[kBfQ], qy[kBfQ], qz[kBfQ], bd[kBfQ];
-    int bi[kBfQ];
+    double qx[NQ], qy[NQ], qz[NQ], bd[NQ];
+    int bi[NQ];
 #pragma unroll
-    for (int j = 0; j < kBfQ; j++) {
+    for (int j = 0; j < NQ; j++) {
         const int64_t qi = min(q0 + j, nq - 1);
         qx[j] = q[3 * qi]; qy[j] = q[3 * qi + 1]; qz[j] = q[3 * qi + 2];
         bd[j] = 1.0e300; bi[j] = 0x7fffffff;
@@ -133,7 +148,7 @@ __global__ void __launch_bounds__(kBfTpb) k_bf_knn1(const double *__restrict__ t
         for (int i = tid; i < kBfTile; i += kBfTpb) {
             const double tx = tile[3 * i], ty = tile[3 * i + 1], tz = tile[3 * i + 2];
 #pragma unroll
-            for (int j = 0; j < kBfQ; j++) {
+            for (int j = 0; j < NQ; j++) {
                 const double d = l2_exact(qx[j], qy[j], qz[j], tx, ty, tz);
                 if (bf_less(d, base + i, bd[j], bi[j])) { bd[j] = d; bi[j] = base + i; }
             }
@@ -146,14 +161,14 @@ __global__ void __launch_bounds__(kBfTpb) k_bf_knn1(const double *__restrict__ t
     for (int64_t i = p_begin + (int64_t)nfull * kBfTile + tid; i < p_end; i += kBfTpb) {
         const double tx = tgt[3 * i], ty = tgt[3 * i + 1], tz = tgt[3 * i + 2];
 #pragma unroll
-        for (int j = 0; j < kBfQ; j++) {
+        for (int j = 0; j < NQ; j++) {
             const double d = l2_exact(qx[j], qy[j], qz[j], tx, ty, tz);
             if (bf_less(d, (int)i, bd[j], bi[j])) { bd[j] = d; bi[j] = (int)i; }
         }
     }
     // per-query minimum over the block: butterflies inside each warp, then one step through shared memory
 #pragma unroll
-    for (int j = 0; j < kBfQ; j++) {
+    for (int j = 0; j < NQ; j++) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             const double od = __shfl_xor_sync(0xffffffffu, bd[j], o);
@@ -163,7 +178,7 @@ __global__ void __launch_bounds__(kBfTpb) k_bf_knn1(const double *__restrict__ t
         if (lane == 0) { red_d[warp][j] = bd[j]; red_i[warp][j] = bi[j]; }
     }
     __syncthreads();
-    if (tid < kBfQ && q0 + tid < nq) {
+    if (tid < NQ && q0 + tid < nq) {
         double d = red_d[0][tid];
         int i = red_i[0][tid];
         for (int w = 1; w < kBfTpb / 32; w++)
@@ -173,21 +188,32 @@ __global__ void __launch_bounds__(kBfTpb) k_bf_knn1(const double *__restrict__ t
     }
 }
 
+// one warp per query: the lanes stride over the slices' minima (one thread walking 296 dependent loads took
+// longer than the search itself), then a butterfly
 __global__ void __launch_bounds__(256) k_bf_merge(const double *__restrict__ part_d2, const int *__restrict__ part_idx,
                                                   int nslices, int64_t nq, double r2, int *__restrict__ out_idx,
                                                   double *__restrict__ out_d2) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    double d = part_d2[i];
-    int b = part_idx[i];
-    for (int s2 = 1; s2 < nslices; s2++) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= nq) return;  // warp-uniform
+    double d = 1.0e300;
+    int b = 0x7fffffff;
+    for (int s2 = lane; s2 < nslices; s2 += 32) {
         const double od = part_d2[(int64_t)s2 * nq + i];
         const int oi = part_idx[(int64_t)s2 * nq + i];
         if (bf_less(od, oi, d, b)) { d = od; b = oi; }
     }
-    const bool hit = b != 0x7fffffff && d < r2;  // accepted iff d2 < (double)(float)(r*r) (KDTreeFlann.cpp:185)
-    out_idx[i] = hit ? b : -1;
-    out_d2[i] = hit ? d : 0.0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, d, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, b, o);
+        if (bf_less(od, oi, d, b)) { d = od; b = oi; }
+    }
+    if (lane == 0) {
+        const bool hit = b != 0x7fffffff && d < r2;  // accepted iff d2 < (double)(float)(r*r) (KDTreeFlann.cpp:185)
+        out_idx[i] = hit ? b : -1;
+        out_d2[i] = hit ? d : 0.0;
+    }
 }
 
 int bf_launch(const double *d_tgt, int64_t n, const double *d_q, int64_t nq, double radius, int *d_idx, double *d_d2,
@@ -196,7 +222,10 @@ int bf_launch(const double *d_tgt, int64_t n, const double *d_q, int64_t nq, dou
     if ((reinterpret_cast<uintptr_t>(d_tgt) & 15) != 0) return VB200_ERR_INVALID;  // the bulk copies need 16-byte alignment
     if (nq == 0) return VB200_OK;
     const double r2 = (double)(float)(radius * radius);
-    const int nchunks = div_up(nq, kBfQ);
+    // queries per block: 8, or fewer when there are fewer (1-2 queries leave the kernel bound by the HBM stream,
+    // 8 by the FP64 pipe)
+    const int cq = nq >= 5 ? 8 : nq >= 3 ? 4 : (int)nq;
+    const int nchunks = div_up(nq, cq);
     if (nchunks > 65535) return VB200_ERR_INVALID;  // grid.y; 524 280 queries per call
     // enough blocks for two waves when there are few queries; slices are whole tiles so every bulk copy starts
     // on a 16-byte boundary (1024 points x 24 B)
@@ -208,13 +237,27 @@ int bf_launch(const double *d_tgt, int64_t n, const double *d_q, int64_t nq, dou
     VB_CUDA(p_d2.alloc((size_t)nslices * (size_t)nq));
     VB_CUDA(p_idx.alloc((size_t)nslices * (size_t)nq));
     const size_t smem = (size_t)kBfStages * kBfTileBytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VB_CUDA(cudaFuncSetAttribute(k_bf_knn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+    // the opt-in for > 48 KB of dynamic shared memory is per device and per kernel: once each
+    static bool opted[64][4] = {};
+    int dev = 0;
+    VB_CUDA(cudaGetDevice(&dev));
+    const int variant = cq == 1 ? 0 : cq == 2 ? 1 : cq == 4 ? 2 : 3;
+    auto launch = [&](auto kernel) -> cudaError_t {
+        if (dev >= 64 || !opted[dev][variant]) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            if (dev < 64) opted[dev][variant] = true;
+        }
+        kernel<<<dim3((unsigned)nslices, (unsigned)nchunks), kBfTpb, smem, st>>>(d_tgt, n, slice_pts, d_q, nq, p_d2.p, p_idx.p);
+        return cudaSuccess;
+    };
+    switch (cq) {
+        case 1: VB_CUDA(launch(k_bf_knn1<1>)); break;
+        case 2: VB_CUDA(launch(k_bf_knn1<2>)); break;
+        case 4: VB_CUDA(launch(k_bf_knn1<4>)); break;
+        default: VB_CUDA(launch(k_bf_knn1<8>)); break;
     }
-    k_bf_knn1<<<dim3((unsigned)nslices, (unsigned)nchunks), kBfTpb, smem, st>>>(d_tgt, n, slice_pts, d_q, nq, p_d2.p, p_idx.p);
-    k_bf_merge<<<div_up(nq, 256), 256, 0, st>>>(p_d2.p, p_idx.p, (int)nslices, nq, r2, d_idx, d_d2);
+    k_bf_merge<<<div_up(nq * 32, 256), 256, 0, st>>>(p_d2.p, p_idx.p, (int)nslices, nq, r2, d_idx, d_d2);
     VB_CUDA(cudaGetLastError());
     return VB200_OK;
 }
@@ -227,8 +270,10 @@ int knn1_launch(Scene *sc, const double *d_q, int64_t nq, double radius, int *d_
     if (nq > 0x7fffffff) return VB200_ERR_INVALID;
     const double r2 = (double)(float)(radius * radius);  // KDTreeFlann.cpp:185
     if (nq <= kWarpPerQueryMax) {
+        // dev knob VB200_KNN_WPQ=seq: the sequential cell walk instead of the breadth-first one (same results)
+        static const int bfs = []() { const char *e = getenv("VB200_KNN_WPQ"); return !(e && e[0] == 's'); }();
         k_knn1_wpq<<<div_up(nq * 32, kTpb), kTpb, 0, sc->stream>>>(sc->grid, d_q, nq, r2,
-                                                                   r2_upper_bound(sc->grid.p, r2), d_idx, d_d2);
+                                                                   r2_upper_bound(sc->grid.p, r2), bfs, d_idx, d_d2);
         VB_CUDA(cudaGetLastError());
         return VB200_OK;
     }

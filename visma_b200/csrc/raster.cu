@@ -176,7 +176,10 @@ struct __align__(16) CovItem {
     int pix;           // j * W + i
 };
 
-constexpr int kTrisTpb = 128;
+#ifndef VB_TRIS_TPB
+#define VB_TRIS_TPB 128
+#endif
+constexpr int kTrisTpb = VB_TRIS_TPB;  // the warps of a block are independent (no block barrier)
 
 // Clipped polygons (rare): clip, snap, and queue the fan triangles for k_big.
 __device__ __noinline__ void tri_setup_clipped(float4 c0, float4 c1, float4 c2, int mesh, int H, int W,
@@ -310,7 +313,7 @@ __device__ __forceinline__ void shade_item(const CovItem &it, const TriRec &r, i
     atomicMin(zbuf + (size_t)(r.mesh_tl >> 3) * H * W + it.pix, (unsigned)qi);  // GL_LESS
 }
 
-__global__ void __launch_bounds__(kTrisTpb, 8) k_tris(const MeshDesc *__restrict__ meshes, const int *__restrict__ tri_mesh_start,
+__global__ void __launch_bounds__(kTrisTpb, 1024 / kTrisTpb) k_tris(const MeshDesc *__restrict__ meshes, const int *__restrict__ tri_mesh_start,
                                                    int n_mesh, int64_t n_tri_total, const float *__restrict__ V,
                                                    const int *__restrict__ F, int H, int W, unsigned *__restrict__ zbuf,
                                                    TriSetup *__restrict__ big, int *__restrict__ big_count) {
