@@ -33,6 +33,11 @@ namespace vb {
 
 namespace {
 
+// Part B of the pass runs over a worklist of the blocks that listed anything (k_pass_b_wl) unless the older
+// one-block-per-(block, warp) launch is asked for (-DVB_PB_PER_BLOCK; the fused iteration tail needs it too).
+#if !defined(VB_PB_PER_BLOCK) && !defined(VB_FUSE_SOLVE) && !defined(VB_PB_WORKLIST)
+#define VB_PB_WORKLIST
+#endif
 #ifndef VB_PASS_TPB
 #define VB_PASS_TPB 128
 #endif
@@ -81,7 +86,15 @@ struct PassParams {
     float slack;    // how far beyond the answer's reach a search looks, so that its result survives small moves
     float pos_err;  // bound on the error of a distance between two centred-f32 query positions
     int use_cache;  // 0: every point is searched in every pass (dev knob VB200_NN_CACHE=0: the ablation bench.py reports)
+#ifdef VB_PB_WORKLIST
+    int *work;      // part-A blocks that listed anything in this pass, in order of arrival
+    int *work_ctr;  // [parity][2]: {blocks listed, part-B items handed out}; passes alternate between the two pairs
+    int parity;
+#endif
 };
+#if defined(VB_PB_WORKLIST) && defined(VB_FUSE_SOLVE)
+#error "the worklist part B has no fused iteration tail"
+#endif
 
 #ifndef VB_SLACK_PCT
 #define VB_SLACK_PCT 8
@@ -227,9 +240,16 @@ struct PassCtx {
         const double *t = G.xyz + 3 * (int64_t)bs;
         const double vt[3] = {t[0], t[1], t[2]};
         const double d2 = l2_exact(vs[0], vs[1], vs[2], vt);
+        return row_known(bs, vt, d2, vs, r2, x);
+    }
+
+    // the same from a target point already loaded and its exact distance
+    // (nt_loaded: the target normal when the caller has fetched it already, alongside the point)
+    __device__ __forceinline__ bool row_known(int bs, const double (&vt)[3], double d2, const double (&vs)[3], double r2,
+                                              double (&x)[8], const double *nt_loaded = nullptr) {
         if (!(d2 < r2)) return false;
         if (MODE == 1) {
-            const double *nn = G.nrm + 3 * (int64_t)bs;
+            const double *nn = nt_loaded ? nt_loaded : G.nrm + 3 * (int64_t)bs;
             const double nt[3] = {nn[0], nn[1], nn[2]};
             x[0] = vs[1] * nt[2] - vs[2] * nt[1];
             x[1] = vs[2] * nt[0] - vs[0] * nt[2];
@@ -307,6 +327,13 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
     int *__restrict__ hard_cnt, PassParams pp) {
     const BlockTask task = tasks[blockIdx.x];
     const ProbState *st = states + task.prob;
+#ifdef VB_PB_WORKLIST
+    // the counters the NEXT pass will use: idle since the previous pass's part B finished
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        pp.work_ctr[2 * (pp.parity ^ 1)] = 0;
+        pp.work_ctr[2 * (pp.parity ^ 1) + 1] = 0;
+    }
+#endif
     if (st->done) return;
     __shared__ __align__(16) double rows_sh[kPassWarps][32 * kRowStride];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -329,7 +356,59 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
                 corr_s[slot] = -1;  // farther than a cell outside the grid: no neighbour within the radius
             } else {
                 hard = true;
-#ifndef VB_NO_NN_CACHE
+#if defined(VB_PA_NOHI) && !defined(VB_NO_NN_CACHE)
+                // The cached-neighbour test without the f32 screening array: how far the point has moved since
+                // its last search is known from the streamed cache entry alone, and unless that is less than
+                // the entry's bound nothing below can succeed — no gather at all for such a point (every point,
+                // in an alignment's first iterations).  Otherwise the match's exact coordinates are needed
+                // anyway: |q - b| comes from them in double (rounded up to f32: tighter than the screening
+                // distance + band), one level of dependent loads fewer and one 32-byte sector per point less.
+                const int prior = pp.use_cache ? corr_s[slot] : -1;
+                if (prior >= 0) {
+                    const NNCache m = cache[slot];
+                    const float mx = c.qx - m.qx, my = c.qy - m.qy, mz = c.qz - m.qz;
+                    const float mv = sqrtf(fmaf(mz, mz, fmaf(my, my, mx * mx))) * 1.000001f + pp.pos_err;
+                    const float lim = sqrtf(fabsf(m.sec)) * 0.999999f;  // NaN (no cache) compares false
+                    if (mv < lim) {
+                        const double *tp = G.xyz + 3 * (int64_t)prior;
+                        const double vt[3] = {tp[0], tp[1], tp[2]};
+                        // (the normal is fetched with the point, not after the test: a point that gets here
+                        // nearly always passes, and the two gathers then overlap)
+                        double nt[3] = {0.0, 0.0, 0.0};
+                        if (MODE == 1 && m.sec >= 0.0f) {
+                            const double *np = G.nrm + 3 * (int64_t)prior;
+                            nt[0] = np[0]; nt[1] = np[1]; nt[2] = np[2];
+                        }
+                        const double da = l2_exact(vs[0], vs[1], vs[2], vt);
+                        if (m.sec >= 0.0f) {
+                            // |q - b| (upper bound) + move (upper bound) < distance to anything else then (lower bound)
+                            if (sqrtf(__double2float_ru(da)) * 1.000001f + mv < lim) {
+                                hard = false;
+                                // still the nearest, but it may have left the radius: then there is no
+                                // correspondence (and nothing to remember: corr_s doubles as the list)
+                                if (!ctx.row_known(prior, vt, da, vs, pp.r2, x, MODE == 1 ? nt : nullptr)) corr_s[slot] = -1;
+                            }
+                        } else {
+                            // a two-candidate entry: if both are still nearer than anything else can be, the
+                            // winner between them is taken in double
+                            const int other = second_s[slot];
+                            if (other >= 0) {
+                                const double *up = G.xyz + 3 * (int64_t)other;
+                                const double vu[3] = {up[0], up[1], up[2]};
+                                const double db = l2_exact(vs[0], vs[1], vs[2], vu);
+                                if (sqrtf(__double2float_ru(fmax(da, db))) * 1.000001f + mv < lim) {
+                                    hard = false;
+                                    const bool first = da < db || (da == db && __ldg(G.orig + prior) < __ldg(G.orig + other));
+                                    if (!first) { corr_s[slot] = other; second_s[slot] = prior; }
+                                    const bool ok = first ? ctx.row_known(prior, vt, da, vs, pp.r2, x)
+                                                          : ctx.row_known(other, vu, db, vs, pp.r2, x);
+                                    if (!ok) corr_s[slot] = -1;
+                                }
+                            }
+                        }
+                    }
+                }
+#elif !defined(VB_NO_NN_CACHE)
                 const int prior = pp.use_cache ? corr_s[slot] : -1;
                 if (prior >= 0) {
                     const NNCache m = cache[slot];
@@ -405,6 +484,9 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
 #pragma unroll
     for (int w = 0; w < kPassWarps; w++) total += listed[w];
     if (total == 0) out[(kPart / 2) + threadIdx.x] = make_double2(0.0, 0.0);  // 4 rows x 32 double2 = 128 threads
+#ifdef VB_PB_WORKLIST
+    else if (threadIdx.x == 0) pp.work[atomicAdd(pp.work_ctr + 2 * pp.parity, 1)] = blockIdx.x;
+#endif
 }
 
 // entry t of the 32 estimator slots from a summed 8x8 Gram matrix D.  Slot layout: point-to-plane 0..20 JTJ
@@ -547,6 +629,86 @@ __global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b(
     iteration_tail(pd, partials, prob_ctr + task.prob, ws.rows, MODE == 1, states + task.prob, sp, pass_index);
 }
 
+#ifdef VB_PB_WORKLIST
+// ---- pass, part B over a worklist.  k_pass_b above launches one single-warp block per (part-A block, warp):
+// 50 176 blocks on the BASELINE workload, nearly all of which find an empty list once an alignment settles —
+// and the GPU hands out about one block per clock, so those empty blocks alone are ~25 us of every settled pass.
+// Here part A appends the blocks that listed anything to a worklist (one atomic per such block) and part B is a
+// resident grid of single-warp blocks, each of which takes (block, warp) items off the list one at a time (an
+// atomic per item: dynamic balance in the first iterations, when every block is listed) until none is left.
+// Which warp handles an item is arbitrary; what it computes and where it writes (the item's own partial row,
+// the points' own slots) is not: results are bit for bit those of k_pass_b.
+template <int MODE>
+__global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b_wl(
+    GridDev G, const double *__restrict__ src_xyz, const BlockTask *__restrict__ tasks,
+    const ProbState *__restrict__ states, double *partials, int *__restrict__ corr_s,
+    NNCache *__restrict__ cache, int *__restrict__ second_s, const unsigned char *__restrict__ hard_ids,
+    const int *__restrict__ hard_cnt, PassParams pp) {
+    const int lane = threadIdx.x;
+    __shared__ WarpScratch ws;
+    int *ctr = pp.work_ctr + 2 * pp.parity;
+    const int n_items = ctr[0] * kPassWarps;  // final: part A has finished
+#pragma unroll 1
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(ctr + 1, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int blk = pp.work[item / kPassWarps], warp = item % kPassWarps;
+        int seg_end[kPassWarps];
+        int total = 0;
+#pragma unroll
+        for (int w = 0; w < kPassWarps; w++) {
+            total += hard_cnt[blk * kPassWarps + w];
+            seg_end[w] = total;
+        }
+        const BlockTask task = tasks[blk];
+        PassCtx<MODE> ctx(G, states[task.prob].T);  // (a finished problem's blocks are never listed)
+#pragma unroll 1
+        for (int h0 = 32 * warp; h0 < total; h0 += 32 * kPassWarps) {
+            const bool live = h0 + lane < total;
+            double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            double vs[3] = {0, 0, 0}, d2 = 0.0;
+            QueryCtx c;
+            int prior = -1, slot = 0;
+            float slack = 0.0f;
+            if (live) {
+                const int h = h0 + lane;
+                int w = 0, base = 0;
+#pragma unroll
+                for (int i = 0; i < kPassWarps - 1; i++)
+                    if (h >= seg_end[i]) { w = i + 1; base = seg_end[i]; }
+                const int id = hard_ids[((int64_t)blk * kPassWarps + w) * (32 * kPtsPerThread) + (h - base)];
+                const int local = (w * kPtsPerThread + (id >> 5)) * 32 + (id & 31);
+                slot = task.corr_begin + local;
+                ctx.transform(src_xyz + 3 * (int64_t)(task.src_begin + local), vs);
+                make_query(G.p, vs[0], vs[1], vs[2], c);
+                prior = corr_s[slot];
+                const NNCache m = cache[slot];
+                const float mx = c.qx - m.qx, my = c.qy - m.qy, mz = c.qz - m.qz;
+                if (fmaf(mz, mz, fmaf(my, my, mx * mx)) < 4.0f * pp.slack * pp.slack) slack = pp.slack;
+            }
+            float sec = -1.0f;
+            int other = -1;
+            const int bs = nn_search_hybrid<32>(G, live, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, prior, ws.runs, &d2,
+                                                slack, &sec, VB_COOP_WARP_LANES, &other);
+            if (live) {
+                corr_s[slot] = bs;
+                NNCache m;
+                m.qx = c.qx; m.qy = c.qy; m.qz = c.qz;
+                m.sec = bs >= 0 ? sec : -1.0f;
+                cache[slot] = m;
+                second_s[slot] = bs >= 0 ? other : -1;
+                if (bs >= 0) ctx.row_of(bs, vs, pp.r2, x);
+            }
+            ctx.accumulate(ws.rows, x);
+        }
+        ctx.write_partial(partials + ((int64_t)blk * kRowsPerBlock + 1 + warp) * kPart);
+        __syncwarp();
+    }
+}
+#endif
+
 // ---- estimator solves from the reduced slots ---------------------------------------------------------
 __device__ void update_p2plane(const double *tot, const SolveParams &sp, double *U) {
     mat4_identity(U);
@@ -607,11 +769,44 @@ __device__ __forceinline__ void reduce_partials(const ProbDesc &pd, const double
                                                 double (*sw)[kPart], double *tot) {
     const int e = threadIdx.x & (kPart - 1), grp = threadIdx.x / kPart;  // 4 groups of 64 threads
     double s = 0.0;
+    const double *col = partials + (int64_t)pd.blk_begin * kRowsPerBlock * kPart + e;
+#ifdef VB_SOLVE_SKIP
+    // Part-B rows of blocks whose list was empty are zeros (k_pass_a wrote them): not loading them leaves every
+    // sum's bits alone (s + 0.0 == s; s is never -0.0) and, once an alignment settles, four fifths of the rows
+    // are such zeros.  Which blocks listed anything is read ONCE per chunk of blocks into shared memory — one
+    // coalesced 16-byte load per block — so no row has a dependent global load in front of it (the first attempt
+    // looked the count up per row and was slower than loading the zeros).  Rows keep their group and their
+    // position in the chain of adds: a chunk is a whole number of 64-row steps.
+    constexpr int kFlagChunk = 2048;  // blocks per chunk
+    static_assert(kPassWarps == 4 && (kFlagChunk * kRowsPerBlock) % (4 * 16) == 0, "chunk = whole unrolled steps");
+    __shared__ unsigned char listed[kFlagChunk];
+    for (int c0 = 0; c0 < pd.blk_count; c0 += kFlagChunk) {
+        const int nb = min(kFlagChunk, pd.blk_count - c0);
+        __syncthreads();  // the previous chunk's flags have been consumed
+        for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+            const int4 h = reinterpret_cast<const int4 *>(hard_cnt)[pd.blk_begin + c0 + j];
+            listed[j] = (h.x | h.y | h.z | h.w) != 0;
+        }
+        __syncthreads();
+        const int r0 = c0 * kRowsPerBlock, r1 = r0 + nb * kRowsPerBlock;
+        for (int b = r0 + grp; b < r1; b += 4 * 16) {
+            double v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int r = b + 4 * i;
+                const int blk = r / kRowsPerBlock;
+                const bool need = r < r1 && (r == blk * kRowsPerBlock || listed[min(blk - c0, kFlagChunk - 1)]);
+                v[i] = need ? col[(int64_t)r * kPart] : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) s += v[i];
+        }
+    }
+#else
     // rows in index order per group.  (Skipping the part-B rows of blocks with an empty list was measured
     // slower: the count lookup puts a dependent load in front of every row.)
     (void)hard_cnt;
     // 16 independent loads in flight per thread (the rows sit in L2; the chain of adds keeps its fixed order)
-    const double *col = partials + (int64_t)pd.blk_begin * kRowsPerBlock * kPart + e;
     const int nrows = pd.blk_count * kRowsPerBlock;
     // (the ragged last batch is predicated, not a loop of dependent loads: adding +0.0 leaves the sum's bits alone)
     for (int b = grp; b < nrows; b += 4 * 16) {
@@ -621,6 +816,7 @@ __device__ __forceinline__ void reduce_partials(const ProbDesc &pd, const double
 #pragma unroll
         for (int i = 0; i < 16; i++) s += v[i];
     }
+#endif
     sw[grp][e] = s;
     __syncthreads();
     if (threadIdx.x < kPart) sw[0][e] = ((sw[0][e] + sw[1][e]) + sw[2][e]) + sw[3][e];
@@ -894,6 +1090,11 @@ struct Batch {
     int *d_hard_cnt = nullptr;
     int *d_prob_ctr = nullptr;               // per problem: part-B warps finished in the current pass
     int *d_ndone = nullptr;                  // problems finished since set_problems
+#ifdef VB_PB_WORKLIST
+    int *d_work = nullptr;                   // part-A blocks with a non-empty list (k_pass_b_wl)
+    int *d_work_ctr = nullptr;               // 2 x {listed, handed out}
+    int pass_parity = 0;
+#endif
     int64_t launches = 0;
     int iter_base = 0;                       // running pass index for vb200_batch_iterate
     double *d_totals = nullptr;              // P x kAcc, library-owned unless the caller supplied a buffer
@@ -912,6 +1113,11 @@ static void batch_free_problems(Batch *b) {
     b->d_second = nullptr;
     if (b->d_ndone) cudaFreeAsync(b->d_ndone, st);
     b->d_ndone = nullptr;
+#ifdef VB_PB_WORKLIST
+    if (b->d_work) cudaFreeAsync(b->d_work, st);
+    if (b->d_work_ctr) cudaFreeAsync(b->d_work_ctr, st);
+    b->d_work = nullptr; b->d_work_ctr = nullptr;
+#endif
     b->d_totals = nullptr; b->d_npts_global = nullptr; b->d_cache = nullptr;
     b->d_hard_ids = nullptr; b->d_hard_cnt = nullptr; b->d_prob_ctr = nullptr;
     for (void *q : ptrs)
@@ -1044,6 +1250,12 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
     VB_CUDA(cudaMemsetAsync(b->d_prob_ctr, 0, sizeof(int) * (size_t)std::max(P, 1), st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_ndone, sizeof(int), st));
     VB_CUDA(cudaMemsetAsync(b->d_ndone, 0, sizeof(int), st));
+#ifdef VB_PB_WORKLIST
+    VB_CUDA(cudaMallocAsync((void **)&b->d_work, sizeof(int) * (size_t)std::max(b->nblk, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_work_ctr, sizeof(int) * 4, st));
+    VB_CUDA(cudaMemsetAsync(b->d_work_ctr, 0, sizeof(int) * 4, st));
+    b->pass_parity = 0;
+#endif
     VB_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
     return VB200_OK;
 }
@@ -1051,9 +1263,33 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
 
 // one correspondence pass = part A (every point, streaming) + part B (the points that need a search).  With
 // `sp` given, part B also finishes the iteration (reduction + estimator step by each problem's last warp).
-static void launch_pass(Batch *b, bool plane, const PassParams &pp, const SolveParams *sp = nullptr, int pass_index = 0) {
+static void launch_pass(Batch *b, bool plane, const PassParams &pp_in, const SolveParams *sp = nullptr, int pass_index = 0) {
     Scene *sc = b->scene;
     cudaStream_t st = b->stream;
+#ifdef VB_PB_WORKLIST
+    PassParams pp = pp_in;
+    pp.work = b->d_work;
+    pp.work_ctr = b->d_work_ctr;
+    pp.parity = b->pass_parity;
+    b->pass_parity ^= 1;
+    (void)sp; (void)pass_index;
+    const int nwarps = std::min(b->nblk * kPassWarps, kNumSMsB200 * 4 * VB_PASS_MINBLOCKS);
+    if (plane) {
+        k_pass_a<1><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
+                                                  b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp);
+        k_pass_b_wl<1><<<nwarps, 32, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
+                                              b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp);
+    } else {
+        k_pass_a<0><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
+                                                  b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp);
+        k_pass_b_wl<0><<<nwarps, 32, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
+                                              b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp);
+    }
+    b->launches += 2;
+    return;
+#else
+    const PassParams &pp = pp_in;
+#endif
     SolveParams s0;
     memset(&s0, 0, sizeof(s0));
     const SolveParams &s = sp ? *sp : s0;
