@@ -631,9 +631,8 @@ __global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b(
 
 #ifdef VB_PB_WORKLIST
 // ---- pass, part B over a worklist.  k_pass_b above launches one single-warp block per (part-A block, warp):
-// 50 176 blocks on the BASELINE workload, nearly all of which find an empty list once an alignment settles —
-// and the GPU hands out about one block per clock, so those empty blocks alone are ~25 us of every settled pass.
-// Here part A appends the blocks that listed anything to a worklist (one atomic per such block) and part B is a
+// 12 544 blocks on the BASELINE workload, nearly all of which find an empty list once an alignment settles, and
+// in the first iterations the block scheduler's fixed order leaves a tail.  Here part A appends the blocks that listed anything to a worklist (one atomic per such block) and part B is a
 // resident grid of single-warp blocks, each of which takes (block, warp) items off the list one at a time (an
 // atomic per item: dynamic balance in the first iterations, when every block is listed) until none is left.
 // Which warp handles an item is arbitrary; what it computes and where it writes (the item's own partial row,
