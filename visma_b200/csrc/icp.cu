@@ -410,7 +410,21 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
                 }
 #elif !defined(VB_NO_NN_CACHE)
                 const int prior = pp.use_cache ? corr_s[slot] : -1;
+#ifdef VB_PA_PRETEST
+                // how far the point has moved since its last search is known from the streamed cache entry alone:
+                // unless that is less than the entry's bound neither test below can succeed, and the gather of
+                // the match is skipped (every point, in an alignment's first iterations)
+                bool may_hold = false;
                 if (prior >= 0) {
+                    const NNCache m0 = cache[slot];
+                    const float ax = c.qx - m0.qx, ay = c.qy - m0.qy, az = c.qz - m0.qz;
+                    may_hold = sqrtf(fmaf(az, az, fmaf(ay, ay, ax * ax))) * 1.000001f + pp.pos_err <
+                               sqrtf(fabsf(m0.sec)) * 0.999999f;  // NaN (no cache) compares false
+                }
+                if (may_hold) {
+#else
+                if (prior >= 0) {
+#endif
                     const NNCache m = cache[slot];
                     const float4 t = __ldg(G.hi + prior);
                     const float dx = c.qx - t.x, dy = c.qy - t.y, dz = c.qz - t.z;
@@ -805,15 +819,20 @@ __device__ __forceinline__ void reduce_partials(const ProbDesc &pd, const double
     // rows in index order per group.  (Skipping the part-B rows of blocks with an empty list was measured
     // slower: the count lookup puts a dependent load in front of every row.)
     (void)hard_cnt;
-    // 16 independent loads in flight per thread (the rows sit in L2; the chain of adds keeps its fixed order)
+    // kSolveInflight independent loads in flight per thread (the rows sit in L2; the chain of adds keeps its fixed
+    // order whatever the batch size, so this knob never changes a bit of the result)
+#ifndef VB_SOLVE_INFLIGHT
+#define VB_SOLVE_INFLIGHT 16
+#endif
+    constexpr int kSolveInflight = VB_SOLVE_INFLIGHT;
     const int nrows = pd.blk_count * kRowsPerBlock;
     // (the ragged last batch is predicated, not a loop of dependent loads: adding +0.0 leaves the sum's bits alone)
-    for (int b = grp; b < nrows; b += 4 * 16) {
-        double v[16];
+    for (int b = grp; b < nrows; b += 4 * kSolveInflight) {
+        double v[kSolveInflight];
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = b + 4 * i < nrows ? col[(int64_t)(b + 4 * i) * kPart] : 0.0;
+        for (int i = 0; i < kSolveInflight; i++) v[i] = b + 4 * i < nrows ? col[(int64_t)(b + 4 * i) * kPart] : 0.0;
 #pragma unroll
-        for (int i = 0; i < 16; i++) s += v[i];
+        for (int i = 0; i < kSolveInflight; i++) s += v[i];
     }
 #endif
     sw[grp][e] = s;
