@@ -63,3 +63,21 @@ libc.srand(0)
 stream = np.array([libc.rand() for _ in range(300)], np.int64)
 np.savez_compressed(os.path.join(OUT, "unit_rand.npz"), rand=stream, rand_max=np.int64(RAND_MAX))
 print("unit_rand:", stream[:3])
+
+# A second real-data pair: cloud_bin_2 -> cloud_bin_1 from the pairwise initial alignment the reference ships
+# (examples/TestData/ICP/init.log, entry "1 2": the transformation that brings fragment 2 into fragment 1's
+# frame).  No published numbers exist for it: the expected outputs are the unmodified reference's (oracle/_ref).
+s2, s2n = read_pcd(d + "cloud_bin_2.pcd")
+log = open(d + "init.log").read().split()
+k = [i for i in range(0, len(log), 19) if log[i] == "1" and log[i + 1] == "2"][0]
+init12 = np.array([float(x) for x in log[k + 3:k + 19]]).reshape(4, 4)
+s2_64, s2n_64 = s2.astype(np.float64), s2n.astype(np.float64)
+ev = pyref.evaluate_registration(s2_64, t64, 0.02, init12)
+p2p = pyref.registration_icp(s2_64, t64, 0.02, init12, pyref.P2P)
+p2l = pyref.registration_icp(s2_64, t64, 0.02, init12, pyref.P2PLANE, src_nrm=s2n_64, tgt_nrm=tn64)
+np.savez_compressed(
+    os.path.join(OUT, "icp_pair12.npz"), src=s2, init=init12,
+    ref_eval=np.array([ev["fitness"], ev["rmse"], ev["ncorr"]]),
+    ref_p2p=np.array([p2p["fitness"], p2p["rmse"], p2p["ncorr"]]), ref_p2p_T=p2p["T"],
+    ref_p2l=np.array([p2l["fitness"], p2l["rmse"], p2l["ncorr"]]), ref_p2l_T=p2l["T"])
+print("icp_pair12:", ev["fitness"], ev["ncorr"], p2p["fitness"], p2p["ncorr"], p2l["fitness"], p2l["ncorr"])

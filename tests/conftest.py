@@ -41,6 +41,14 @@ def kat():
 
 
 @pytest.fixture(scope="session")
+def pair12():
+    """cloud_bin_2 -> cloud_bin_1 from the reference's examples/TestData/ICP/init.log entry "1 2"; expected
+    outputs = the unmodified reference's (scripts/make_golden.py)."""
+    d = np.load(os.path.join(GOLDEN, "icp_pair12.npz"))
+    return {k: d[k] for k in d.files}
+
+
+@pytest.fixture(scope="session")
 def unit_rand():
     d = np.load(os.path.join(GOLDEN, "unit_rand.npz"))
     return d["rand"].astype(np.float64), float(d["rand_max"])

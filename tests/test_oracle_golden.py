@@ -137,3 +137,22 @@ def test_unorm24_to_float_identity():
     that of the exact division (what the oracle computes) for EVERY 24-bit depth value."""
     q = np.arange(0, 1 << 24, dtype=np.float64)
     assert ((q / 16777215.0).astype(np.float32) == (q * (1.0 / 16777215.0)).astype(np.float32)).all()
+
+
+def test_second_real_pair_against_compiled_reference(oracle, kat, pair12):
+    """cloud_bin_2 -> cloud_bin_1 from the pairwise initial alignment in
+    examples/TestData/ICP/init.log.  The reference publishes no numbers for this pair; the fixture holds the
+    outputs of the unmodified reference compiled here (Registration.cpp:141-186 through oracle/_ref)."""
+    s, t, tn = pair12["src"].astype(np.float64), kat["tgt"].astype(np.float64), kat["tgt_nrm"].astype(np.float64)
+    ix = oracle.Index(t, 0.02)
+    ev = ix.registration_icp(s, 0.02, pair12["init"], oracle.P2P, max_iter=0)
+    assert ev["ncorr"] == int(pair12["ref_eval"][2]) and ev["fitness"] == pair12["ref_eval"][0]
+    assert abs(ev["rmse"] - pair12["ref_eval"][1]) < 1e-12
+    r = ix.registration_icp(s, 0.02, pair12["init"], oracle.P2P)
+    assert r["ncorr"] == int(pair12["ref_p2p"][2])
+    assert abs(r["fitness"] - pair12["ref_p2p"][0]) < 1e-12 and abs(r["rmse"] - pair12["ref_p2p"][1]) < 1e-12
+    assert np.allclose(r["T"], pair12["ref_p2p_T"], atol=1e-11)
+    r = ix.registration_icp(s, 0.02, pair12["init"], oracle.P2PLANE, src_nrm=s, tgt_nrm=tn)
+    assert r["ncorr"] == int(pair12["ref_p2l"][2])
+    assert abs(r["fitness"] - pair12["ref_p2l"][0]) < 1e-12 and abs(r["rmse"] - pair12["ref_p2l"][1]) < 1e-12
+    assert np.allclose(r["T"], pair12["ref_p2l_T"], atol=1e-11)
