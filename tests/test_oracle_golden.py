@@ -156,3 +156,28 @@ def test_second_real_pair_against_compiled_reference(oracle, kat, pair12):
     assert r["ncorr"] == int(pair12["ref_p2l"][2])
     assert abs(r["fitness"] - pair12["ref_p2l"][0]) < 1e-12 and abs(r["rmse"] - pair12["ref_p2l"][1]) < 1e-12
     assert np.allclose(r["T"], pair12["ref_p2l_T"], atol=1e-11)
+
+
+TRANSFORM_REF = np.array([
+    [398.225124, 1205.693071, 881.868153], [321.838886, 1085.294390, 831.611417],
+    [270.900608, 823.791432, 409.198658], [339.937683, 1004.432856, 615.608467],
+    [425.227547, 1157.793590, 484.511386], [434.350931, 1342.432421, 967.169396],
+    [140.844202, 447.193004, 190.052250], [293.388019, 767.506059, 320.900694],
+    [135.193922, 410.559494, 195.502569], [276.542855, 807.338946, 221.948633]])
+# thirdparty/Open3D/src/UnitTest/Core/Geometry/PointCloud.cpp:174-186 (points; the normals are these minus the
+# translation column, :188-200)
+
+
+def test_transform_golden(oracle, unit_rand):
+    """PointCloud::Transform's golden vector (PointCloud.cpp:172-235): p <- rows 0..2 of T [p, 1], no perspective
+    divide even though the unit test's last row is not (0, 0, 0, 1).  The oracle applies its transform inside the
+    ICP loop, so it is observed there: with the golden points as target and the test's matrix as `init`, the
+    initial pass must pair every source point with its own golden image at ~1e-6 (the vector's precision)."""
+    pts = unit_points(unit_rand, 10, 1000.0)
+    T = np.array([[0.10, 0.20, 0.30, 0.40], [0.50, 0.60, 0.70, 0.80], [0.90, 0.10, 0.11, 0.12],
+                  [0.13, 0.14, 0.15, 0.16]])
+    assert np.allclose(pts @ T[:3, :3].T + T[:3, 3], TRANSFORM_REF, atol=1e-6)  # the convention the tests use
+    ix = oracle.Index(TRANSFORM_REF, 1.0)
+    r = ix.registration_icp(pts, 1e-3, T, oracle.P2P, max_iter=0, want_corr=True)
+    assert r["ncorr"] == 10 and r["rmse"] < 2e-6
+    assert (r["corr"][:, 0] == r["corr"][:, 1]).all()
