@@ -1,6 +1,12 @@
 #!/bin/bash
 # dev tool: A/B alternative builds (build/variants/lib_<name>.so) on the GPU box in one short call:
-#   bench line per build, the ICP GPU tests on the builds named in $TEST, trajectory comparison base vs $CMP.
+#   bench line per build, the GPU tests ($TESTFILES, default ICP + KNN) on the builds named in $TEST, trajectory
+#   comparison base vs each build named in $CMP.  Example (the variants prepared at the end of round 1):
+#     scripts/build_variants.sh pretest "-DVB_PA_PRETEST" infl32 "-DVB_SOLVE_INFLIGHT=32" infl64 "-DVB_SOLVE_INFLIGHT=64" \
+#         xyzn "-DVB_XYZN" xyzn_nohi8 "-DVB_XYZN -DVB_PA_NOHI -DVB_PASS_A_MINBLOCKS=8" perblock "-DVB_PB_PER_BLOCK"
+#     gpurun --timeout 300 -- 'TEST="xyzn pretest" CMP="xyzn pretest infl32" bash scripts/ab_gpu_run.sh r2ab \
+#         pretest infl32 infl64 xyzn xyzn_nohi8 perblock'
+#   (build/variants/ travels with the snapshot: ~4 MB per build; delete it before other calls.)
 tag=${1:-ab}; shift
 out=gpurun_out; mkdir -p $out
 libs="visma_b200/libvisma_b200.so"
@@ -9,7 +15,7 @@ date -u +%T
 timeout 150 python scripts/ab_pass.py $libs > $out/${tag}_ab.txt 2>&1; cut -c1-260 $out/${tag}_ab.txt
 date -u +%T
 for n in $TEST; do
-  VISMA_B200_LIB=$PWD/build/variants/lib_$n.so timeout 60 python -m pytest tests/test_gpu_icp.py -m gpu -x -q 2>&1 | tail -2 | sed "s/^/$n: /"
+  VISMA_B200_LIB=$PWD/build/variants/lib_$n.so timeout 90 python -m pytest ${TESTFILES:-tests/test_gpu_icp.py tests/test_gpu_knn.py} -m gpu -x -q 2>&1 | tail -2 | sed "s/^/$n: /"
 done | tee $out/${tag}_tests.txt
 date -u +%T
 if [ -n "$CMP" ]; then

@@ -42,13 +42,23 @@ struct GridParams {
     float band_a, band_b, band_rel;
 };
 
+// Doubles between consecutive scene points in `xyz` (and in `nrm`).  -DVB_XYZN interleaves the two arrays —
+// point and normal of a scene point in one 48-byte record, `nrm` = `xyz` + 3 — so that a matched row of the
+// point-to-plane pass costs exactly two 32-byte sectors instead of three on average (24-byte records straddle
+// a sector boundary half the time).  Off by default: written after the round's GPU time was spent.
+#ifdef VB_XYZN
+constexpr int kPtStride = 6;
+#else
+constexpr int kPtStride = 3;
+#endif
+
 struct GridDev {
     GridParams p;
     const CoarseCell *coarse;
     const int *fstart;
     const float4 *hi;
-    const double *xyz;
-    const double *nrm;  // nullable
+    const double *xyz;  // kPtStride doubles per point
+    const double *nrm;  // nullable; kPtStride doubles per point (VB_XYZN: xyz + 3)
     const int *orig;
     int64_t n;
 };
@@ -235,7 +245,7 @@ static __device__ __noinline__ int nn_exact_rescan(const GridDev &G, const Query
     auto visit = [&](int s0, int s1, float gap2) {
         if ((double)gap2 > bd) return;
         for (int s = s0; s < s1; ++s) {
-            double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)s);
+            double d = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)s);
             if (d < bd) {
                 bd = d; bs = s; bo = __ldg(G.orig + s);
             } else if (d == bd && bs >= 0) {
@@ -278,7 +288,7 @@ __device__ __forceinline__ int nn_search(const GridDev &G, const QueryCtx &c, do
     float bb = band(g, r.best);
     if (r.second - r.best > bb + band(g, r.second)) {
         // unique f32 winner, and (second starts at r2_ub) it is also clear of the threshold band
-        double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)r.bs);
+        double d = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)r.bs);
         if (d < r2) { *d2_out = d; return r.bs; }
         *d2_out = 0.0;
         return -1;
@@ -484,7 +494,7 @@ __device__ __forceinline__ int nn_decide(const GridDev &G, const Screen &r, cons
     const float bb = band(g, r.best);
     if (r.second - r.best > bb + band(g, r.second)) {
         if (unique) *unique = true;  // r.bs is the true nearest: every other point is farther even in double
-        const double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)r.bs);
+        const double d = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)r.bs);
         if (d < r2) { *d2_out = d; return r.bs; }
         return -1;
     }
@@ -831,8 +841,8 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
             const float m3 = fminf(t.d2, cover);
             const float sec3 = m3 - band(g, m3);  // true d2 of every point other than the two is above this
             if (t.s1 >= 0 && sec3 > t.d0 + band(g, t.d0)) {
-                const double da = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)t.s0);
-                const double db = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)t.s1);
+                const double da = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)t.s0);
+                const double db = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)t.s1);
                 // exact ties break to the lowest ORIGINAL index (the documented rule, as nn_exact_rescan)
                 const bool first = da < db || (da == db && __ldg(G.orig + t.s0) < __ldg(G.orig + t.s1));
                 const double dw = first ? da : db;
@@ -845,7 +855,7 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
         }
     }
     if (unique) {
-        const double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)r.bs);
+        const double d = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)r.bs);
         if (!(d < r2)) return -1;
         *d2_out = d;
         if (sec_out) *sec_out = sec1;
@@ -931,7 +941,7 @@ __device__ __forceinline__ int nn_search_wpq(const GridDev &G, const QueryCtx &c
     int out;
     double d2 = 0.0;
     if (m.second - m.best > bb + band(g, m.second)) {
-        const double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)m.bs);
+        const double d = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)m.bs);
         out = d < r2 ? m.bs : -1;
         d2 = d < r2 ? d : 0.0;
     } else {
@@ -1092,7 +1102,7 @@ __device__ __forceinline__ int nn_search_wpq_bfs(const GridDev &G, const QueryCt
     int out;
     double d2 = 0.0;
     if (m.second - m.best > bb + band(g, m.second)) {
-        const double d = l2_exact(qx, qy, qz, G.xyz + 3 * (int64_t)m.bs);
+        const double d = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)m.bs);
         out = d < r2 ? m.bs : -1;
         d2 = d < r2 ? d : 0.0;
     } else {

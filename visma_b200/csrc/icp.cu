@@ -237,7 +237,7 @@ struct PassCtx {
 
     // the exact decision for match candidate bs (>= 0) and, if accepted, the lane's estimator row
     __device__ __forceinline__ bool row_of(int bs, const double (&vs)[3], double r2, double (&x)[8]) {
-        const double *t = G.xyz + 3 * (int64_t)bs;
+        const double *t = G.xyz + kPtStride * (int64_t)bs;
         const double vt[3] = {t[0], t[1], t[2]};
         const double d2 = l2_exact(vs[0], vs[1], vs[2], vt);
         return row_known(bs, vt, d2, vs, r2, x);
@@ -249,7 +249,7 @@ struct PassCtx {
                                               double (&x)[8], const double *nt_loaded = nullptr) {
         if (!(d2 < r2)) return false;
         if (MODE == 1) {
-            const double *nn = nt_loaded ? nt_loaded : G.nrm + 3 * (int64_t)bs;
+            const double *nn = nt_loaded ? nt_loaded : G.nrm + kPtStride * (int64_t)bs;
             const double nt[3] = {nn[0], nn[1], nn[2]};
             x[0] = vs[1] * nt[2] - vs[2] * nt[1];
             x[1] = vs[2] * nt[0] - vs[0] * nt[2];
@@ -370,13 +370,13 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
                     const float mv = sqrtf(fmaf(mz, mz, fmaf(my, my, mx * mx))) * 1.000001f + pp.pos_err;
                     const float lim = sqrtf(fabsf(m.sec)) * 0.999999f;  // NaN (no cache) compares false
                     if (mv < lim) {
-                        const double *tp = G.xyz + 3 * (int64_t)prior;
+                        const double *tp = G.xyz + kPtStride * (int64_t)prior;
                         const double vt[3] = {tp[0], tp[1], tp[2]};
                         // (the normal is fetched with the point, not after the test: a point that gets here
                         // nearly always passes, and the two gathers then overlap)
                         double nt[3] = {0.0, 0.0, 0.0};
                         if (MODE == 1 && m.sec >= 0.0f) {
-                            const double *np = G.nrm + 3 * (int64_t)prior;
+                            const double *np = G.nrm + kPtStride * (int64_t)prior;
                             nt[0] = np[0]; nt[1] = np[1]; nt[2] = np[2];
                         }
                         const double da = l2_exact(vs[0], vs[1], vs[2], vt);
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
                             // winner between them is taken in double
                             const int other = second_s[slot];
                             if (other >= 0) {
-                                const double *up = G.xyz + 3 * (int64_t)other;
+                                const double *up = G.xyz + kPtStride * (int64_t)other;
                                 const double vu[3] = {up[0], up[1], up[2]};
                                 const double db = l2_exact(vs[0], vs[1], vs[2], vu);
                                 if (sqrtf(__double2float_ru(fmax(da, db))) * 1.000001f + mv < lim) {
@@ -450,8 +450,8 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
                             const float lhs2 = sqrtf(dm + band(G.p, dm)) * 1.000001f + moved * 1.000001f + pp.pos_err;
                             if (lhs2 < sqrtf(-m.sec) * 0.999999f) {
                                 hard = false;
-                                const double da = l2_exact(vs[0], vs[1], vs[2], G.xyz + 3 * (int64_t)prior);
-                                const double db = l2_exact(vs[0], vs[1], vs[2], G.xyz + 3 * (int64_t)other);
+                                const double da = l2_exact(vs[0], vs[1], vs[2], G.xyz + kPtStride * (int64_t)prior);
+                                const double db = l2_exact(vs[0], vs[1], vs[2], G.xyz + kPtStride * (int64_t)other);
                                 const bool first = da < db || (da == db && __ldg(G.orig + prior) < __ldg(G.orig + other));
                                 if (!first) { corr_s[slot] = other; second_s[slot] = prior; }
                                 if (!ctx.row_of(first ? prior : other, vs, pp.r2, x)) corr_s[slot] = -1;

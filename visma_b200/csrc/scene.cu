@@ -112,13 +112,13 @@ __global__ void __launch_bounds__(kTpb) k_gather(GridParams g, const unsigned lo
     if (s >= n) return;
     int i = (int)(unsigned int)skey[s];
     double x = xyz_in[3 * (int64_t)i], y = xyz_in[3 * (int64_t)i + 1], z = xyz_in[3 * (int64_t)i + 2];
-    xyz[3 * s] = x; xyz[3 * s + 1] = y; xyz[3 * s + 2] = z;
+    xyz[kPtStride * s] = x; xyz[kPtStride * s + 1] = y; xyz[kPtStride * s + 2] = z;
     hi[s] = make_float4((float)(x - g.ctr[0]), (float)(y - g.ctr[1]), (float)(z - g.ctr[2]), __int_as_float(i));
     orig[s] = i;
     if (nrm_in) {
-        nrm[3 * s] = nrm_in[3 * (int64_t)i];
-        nrm[3 * s + 1] = nrm_in[3 * (int64_t)i + 1];
-        nrm[3 * s + 2] = nrm_in[3 * (int64_t)i + 2];
+        nrm[kPtStride * s] = nrm_in[3 * (int64_t)i];
+        nrm[kPtStride * s + 1] = nrm_in[3 * (int64_t)i + 1];
+        nrm[kPtStride * s + 2] = nrm_in[3 * (int64_t)i + 2];
     }
 }
 
@@ -224,14 +224,19 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     VB_CUDA(d_coarse.alloc((size_t)ncoarse));
     VB_CUDA(d_fstart.alloc((size_t)nfine + 1));
     VB_CUDA(d_hi.alloc((size_t)n));
-    VB_CUDA(d_xyz.alloc(3 * (size_t)n));
+    VB_CUDA(d_xyz.alloc(kPtStride * (size_t)n));
     VB_CUDA(d_orig.alloc((size_t)n));
+#ifdef VB_XYZN
+    double *const nrm_out = d_xyz.p + 3;  // the second half of every 48-byte record (left unwritten without normals)
+#else
     if (h_nrm) VB_CUDA(d_nrm.alloc(3 * (size_t)n));
+    double *const nrm_out = d_nrm.p;
+#endif
     k_fine_starts<<<div_up(ncoarse, 128), 128, 0, st>>>((int)ncoarse, d_cstart.p, d_skey.p, d_cmask.p,
                                                          d_cbase.p, d_coarse.p, d_fstart.p, nfine, (int)n);
     VB_CUDA(cudaGetLastError());
     k_gather<<<div_up(n, kTpb), kTpb, 0, st>>>(g, d_skey.p, n, d_in_xyz.p, d_in_nrm.p, d_hi.p, d_xyz.p,
-                                               d_nrm.p, d_orig.p);
+                                               nrm_out, d_orig.p);
     VB_CUDA(cudaGetLastError());
     VB_CUDA(cudaStreamSynchronize(st));
 
@@ -239,7 +244,11 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     sc->grid.fstart = d_fstart.take();
     sc->grid.hi = d_hi.take();
     sc->grid.xyz = d_xyz.take();
+#ifdef VB_XYZN
+    sc->grid.nrm = h_nrm ? sc->grid.xyz + 3 : nullptr;
+#else
     sc->grid.nrm = h_nrm ? d_nrm.take() : nullptr;
+#endif
     sc->grid.orig = d_orig.take();
     sc->grid.n = n;
     return VB200_OK;
@@ -288,7 +297,9 @@ void scene_free(Scene *sc) {
     cudaFree((void *)sc->grid.fstart);
     cudaFree((void *)sc->grid.hi);
     cudaFree((void *)sc->grid.xyz);
+#ifndef VB_XYZN
     cudaFree((void *)sc->grid.nrm);
+#endif
     cudaFree((void *)sc->grid.orig);
     if (sc->stream2) cudaStreamDestroy(sc->stream2);
     if (sc->stream) cudaStreamDestroy(sc->stream);
