@@ -3,9 +3,9 @@
 #   bench line per build, the GPU tests ($TESTFILES, default ICP + KNN) on the builds named in $TEST, trajectory
 #   comparison base vs each build named in $CMP.  Example (the variants prepared at the end of round 1):
 #     scripts/build_variants.sh pretest "-DVB_PA_PRETEST" infl32 "-DVB_SOLVE_INFLIGHT=32" infl64 "-DVB_SOLVE_INFLIGHT=64" \
-#         xyzn "-DVB_XYZN" xyzn_nohi8 "-DVB_XYZN -DVB_PA_NOHI -DVB_PASS_A_MINBLOCKS=8" perblock "-DVB_PB_PER_BLOCK"
+#         nbw2 "-DVB_NB_WINDOW=2" nbw4 "-DVB_NB_WINDOW=4" xyzn "-DVB_XYZN" xyzn_nohi8 "-DVB_XYZN -DVB_PA_NOHI -DVB_PASS_A_MINBLOCKS=8" perblock "-DVB_PB_PER_BLOCK"
 #     gpurun --timeout 300 -- 'TEST="xyzn pretest" CMP="xyzn pretest infl32" bash scripts/ab_gpu_run.sh r2ab \
-#         pretest infl32 infl64 xyzn xyzn_nohi8 perblock'
+#         pretest infl32 infl64 nbw2 nbw4 xyzn xyzn_nohi8 perblock'
 #   (build/variants/ travels with the snapshot: ~4 MB per build; delete it before other calls.)
 tag=${1:-ab}; shift
 out=gpurun_out; mkdir -p $out

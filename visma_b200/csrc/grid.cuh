@@ -732,7 +732,19 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
         // scene points around the query — 32 candidate bounds for ~10 instructions each.
         float4 t = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.0f);
         if (valid && prior >= 0) t = __ldg(G.hi + prior);
-#ifndef VB_NO_NEIGHBOUR_BOUNDS
+#if defined(VB_NB_WINDOW)
+        // dev variant: only the previous matches of the lanes within +-VB_NB_WINDOW of this one (the lanes are in
+        // spatial order, so the nearest old matches are mostly the adjacent lanes'): 2W+1 checks instead of up
+        // to 32.  Any real scene point gives a valid bound; lanes without a match hold the far-away sentinel.
+        float nb = 3.0e38f;
+#pragma unroll
+        for (int o = -(VB_NB_WINDOW); o <= (VB_NB_WINDOW); ++o) {
+            const int j = ((threadIdx.x & 31) + o) & 31;
+            const float dx = c.qx - __shfl_sync(FULL, t.x, j), dy = c.qy - __shfl_sync(FULL, t.y, j),
+                        dz = c.qz - __shfl_sync(FULL, t.z, j);
+            nb = fminf(nb, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        }
+#elif !defined(VB_NO_NEIGHBOUR_BOUNDS)
         unsigned have = __ballot_sync(FULL, valid && prior >= 0);
         float nb = 3.0e38f;
         while (have) {
