@@ -202,6 +202,7 @@ def run_ours(args):
     scene_build_s = time.perf_counter() - t0
     clouds = [reg.PointCloud(p, n) for p, n in d["sources"]]
     batch = reg.Batch(scene, clouds)
+    batch.set_option(2, 1)  # split timing
     stream = torch.cuda.ExternalStream(scene.stream(), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -258,10 +259,11 @@ def run_ours(args):
 
     # ablation (informational): the same trajectory with the cached-neighbour test off — every point searched
     # in every pass, the previous match used only as a search bound
-    os.environ["VB200_NN_CACHE"] = "0"
+    from visma_b200 import _lib
+    batch.set_option(_lib.OPT_NN_CACHE, 0)
     batch.set_problems(d["T_init"])
     abl = [sum(one_step(True)) for _ in range(args.steps)]
-    del os.environ["VB200_NN_CACHE"]
+    batch.set_option(_lib.OPT_NN_CACHE, 1)
     abl_ms = float(np.mean(abl))
 
     # the real loop, back to back without flushes (informational: what one RegistrationICP run costs)
@@ -376,7 +378,7 @@ def run_ours(args):
                        "solve_ms": float(np.mean(solve_ms)), "allgather_ms": ag_ms,
                        "ablation_search_every_point_every_pass": {
                            "ms_per_step": abl_ms, "iterations_per_s": world * 1e3 / abl_ms,
-                           "note": "VB200_NN_CACHE=0: no cached-neighbour test; same results"},
+                           "note": "VB200_OPT_NN_CACHE=0: no cached-neighbour test; same results"},
                        "scene_build_s": scene_build_s, "converged_to_ground_truth": ok,
                        "max_pose_err_rad_m": [float(errs[:, 0].max()), float(errs[:, 1].max())]},
             "e2e": {"value": e2e_value, "unit": UNIT,

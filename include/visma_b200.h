@@ -127,8 +127,18 @@ int64_t vb200_batch_launches(const vb200_batch_t *batch);
  * Asynchronous on the scene's stream. */
 int vb200_batch_iterate(vb200_batch_t *batch, int estimator, const double *gravity_axis, double max_dist,
                         int n_iter);
+/* measurement knobs of a batch (never needed for results):
+ *   VB200_OPT_NN_CACHE 0      every point is searched in every pass (the cached-neighbour tests are skipped);
+ *                             results are identical, only slower — the ablation bench.py reports;
+ *   VB200_OPT_SPLIT_TIMING 1  vb200_batch_iterate(..., n_iter = 1) brackets the pass and the solve with CUDA
+ *                             events for vb200_batch_last_kernel_ms (the events keep the kernels of the
+ *                             iteration from overlapping: a diagnostic, off by default). */
+#define VB200_OPT_NN_CACHE 1
+#define VB200_OPT_SPLIT_TIMING 2
+int vb200_batch_set_option(vb200_batch_t *batch, int option, int value);
 /* device time (ms, CUDA events on the scene's stream) of the correspondence-pass kernel launches and of
- * the solve kernel launches issued by the most recent vb200_batch_iterate call; synchronises. */
+ * the solve kernel launches issued by the most recent vb200_batch_iterate call made with
+ * VB200_OPT_SPLIT_TIMING; synchronises. */
 int vb200_batch_last_kernel_ms(vb200_batch_t *batch, float *pass_ms, float *solve_ms);
 
 /* ---- one cloud sharded over several GPUs (ICPRefinement's single global transform, src/evaluation.cpp:
@@ -156,6 +166,22 @@ int vb200_batch_solve(vb200_batch_t *batch, int estimator, const double *gravity
 int vb200_estimate(const double *src_xyz, int64_t m, const double *tgt_xyz, const double *tgt_nrm,
                    int64_t n, const int32_t *corr, int64_t K, int estimator, const double *gravity_axis,
                    int device, double out_T[16]);
+
+/* The same with every cloud already resident on the GPU (d_src_xyz m x 3, d_tgt_xyz / d_tgt_nrm n x 3 doubles,
+ * d_corr K x 2 int32, all DEVICE pointers): the K rows are gathered by the kernel, nothing is marshalled on the
+ * host.  Runs on `cuda_stream` (a cudaStream_t, NULL = default) and synchronises it to return out_T.  Indices in
+ * d_corr are trusted (the host entry validates them). */
+int vb200_estimate_device(const void *d_src_xyz, int64_t m, const void *d_tgt_xyz, const void *d_tgt_nrm,
+                          int64_t n, const void *d_corr, int64_t K, int estimator, const double *gravity_axis,
+                          int device, void *cuda_stream, double out_T[16]);
+
+/* ---- replaces cicp::TransformationEstimationPointToPoint4DoF::ComputeRMSE (src/constrained_ICP.cpp:13-23) and the
+ * identical TransformationEstimationPointToPoint::ComputeRMSE (O3D/src/Core/Registration/TransformationEstimation.cpp:
+ * 35-45): sqrt(sum |s_i - t_j|^2 / K) over the correspondences; 0 when K = 0.  (The ICP loop itself never calls
+ * it: inlier_rmse_ comes from the search's distances, Registration.cpp:68,93.  The point-to-plane override,
+ * TransformationEstimation.cpp:61-73, keeps only its LAST residual — `err = r * r` — and is not reproduced.) */
+int vb200_rmse(const double *src_xyz, int64_t m, const double *tgt_xyz, int64_t n, const int32_t *corr, int64_t K,
+               int device, double *out_rmse);
 
 /* ---- orientation-constrained driver: replaces feh::RegisterModelToScene (src/annotation.cpp:29-64):
  * `level` yaw initialisations Ry(2*pi*i/level), one ICP each (all batched on the GPU), keep the run with
@@ -192,8 +218,10 @@ int vb200_render_depth_batch_ex(const float *V_concat, const int64_t *v_off, con
  * z-buffer.  edge_z_near / edge_z_far are the edge SHADER's linearisation uniforms, which the reference fixes
  * at 0.05 / 2.0 when it builds the shader (renderer.cpp:95-96) independently of the camera.  out_edge /
  * out_mask: n_mesh x H x W uint8 (each nullable); edge = round(255 * soft-thresholded mean neighbour depth
- * difference), 0 on a 5-pixel border and on background; mask = 255 where the mesh covers the pixel (the
- * reference reads a colour buffer no shader wrote — undefined; this is the definition SURVEY §8f proposes). */
+ * difference), 0 on a 5-pixel border and on background; mask follows the reference's polarity: 255 on
+ * BACKGROUND — RenderMask clears the colour buffer to 1.0 and reads GL_RED back (render/renderer.cpp:411-422) —
+ * and 0 where the mesh covers the pixel (undefined in the reference, whose depth shader writes no colour;
+ * defined here as 0 so that the map is the binary mask the header promises, render/renderer.h:93). */
 int vb200_render_edge_mask_batch(const float *V_concat, const int64_t *v_off, const int32_t *F_concat,
                                  const int64_t *f_off, int32_t n_mesh, const float *model_T,
                                  const float view_T[16], float zn, float zf, float fx, float fy, float cx,

@@ -258,6 +258,6 @@ int vo_render_edge(const uint32_t *z24, int H, int W, float zn, float zf, uint8_
 }
 
 int vo_render_mask(const uint32_t *z24, int H, int W, uint8_t *out_mask) {
-    for (size_t p = 0; p < (size_t)H * W; p++) out_mask[p] = z24[p] != ZMAX24 ? 255 : 0;
+    for (size_t p = 0; p < (size_t)H * W; p++) out_mask[p] = z24[p] != ZMAX24 ? 0 : 255;
     return 0;
 }

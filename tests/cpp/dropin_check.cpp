@@ -12,6 +12,8 @@
 #include <vector>
 
 #define VISMA_B200_WITH_CICP
+#include <Eigen/LU>
+
 #include "registration_b200.h"
 #include "renderer_b200.h"
 
@@ -74,6 +76,40 @@ int main(int argc, char **argv) {
         out("\"cicp_plugin\": {\"dT\": %.3e, \"ncorr_ref\": %zu, \"ncorr_mix\": %zu}, ",
                max_abs_diff(ref.transformation_, mix.transformation_), ref.correspondence_set_.size(),
                mix.correspondence_set_.size());
+    }
+    // (2b) the gravity-constrained 4-DoF estimator class: the reference's CPU loop driving the GPU estimator vs
+    // the whole loop on the GPU; and cicp::...4DoF::ComputeRMSE (src/constrained_ICP.cpp:13-23) on the GPU
+    {
+        visma_b200::TransformationEstimationPointToPlaneGravity grav(Eigen::Vector3d(0, 1, 0));
+        auto mix = open3d::RegistrationICP(source, target, max_d, init, grav);
+        auto gpu = visma_b200::RegistrationICP(source, target, max_d, init, grav);
+        Eigen::Matrix4d d = gpu.transformation_ * init.inverse();
+        out("\"gravity\": {\"dT\": %.3e, \"ncorr_mix\": %zu, \"ncorr_gpu\": %zu, \"roll_pitch\": %.3e}, ",
+            max_abs_diff(mix.transformation_, gpu.transformation_), mix.correspondence_set_.size(),
+            gpu.correspondence_set_.size(), std::abs(d(1, 1) - 1.0) + std::abs(d(0, 1)) + std::abs(d(2, 1)));
+        open3d::cicp::TransformationEstimationPointToPoint4DoFB200 gpu_est;
+        auto ref = open3d::RegistrationICP(source, target, max_d, init, p2p);
+        open3d::PointCloud moved = source;
+        moved.Transform(ref.transformation_);
+        const double r_ref = p2p.ComputeRMSE(moved, target, ref.correspondence_set_);
+        const double r_gpu = gpu_est.ComputeRMSE(moved, target, ref.correspondence_set_);
+        out("\"rmse\": {\"ref\": %.17g, \"gpu\": %.17g, \"empty\": %g}, ", r_ref, r_gpu,
+            gpu_est.ComputeRMSE(moved, target, open3d::CorrespondenceSet()));
+    }
+    // (2c) a batch mixing sources with and without normals under point-to-plane: the reference decides per call
+    // (Registration.cpp:152-157), so only the bare source returns RegistrationResult(init)
+    {
+        open3d::PointCloud bare, none;
+        bare.points_ = source.points_;
+        visma_b200::Scene scene(target, max_d);
+        auto res = visma_b200::RegistrationICPBatch({&source, &bare, &none, &source}, scene, max_d,
+                                                    {init, init, init, init}, p2l);
+        auto solo = visma_b200::RegistrationICP(source, target, max_d, init, p2l);
+        out("\"mixed_normals\": {\"with_dT\": %.3e, \"with2_dT\": %.3e, \"bare_dT\": %.3e, \"bare_fitness\": %g, "
+            "\"empty_dT\": %.3e, \"with_ncorr\": %zu}, ",
+            max_abs_diff(res[0].transformation_, solo.transformation_),
+            max_abs_diff(res[3].transformation_, solo.transformation_), max_abs_diff(res[1].transformation_, init),
+            res[1].fitness_, max_abs_diff(res[2].transformation_, init), res[0].correspondence_set_.size());
     }
     // (3) error behaviour: invalid distance and missing normals return RegistrationResult(init)
     {

@@ -32,6 +32,16 @@ def test_cpp_dropin_against_reference(tmp_path):
         assert r[k]["dT"] < 1e-6, r[k]
         assert abs(r[k]["ncorr_ref"] - r[k]["ncorr_gpu"]) <= 2 and abs(r[k]["rmse_ref"] - r[k]["rmse_gpu"]) < 1e-6
     assert r["cicp_plugin"]["dT"] < 1e-9 and r["cicp_plugin"]["ncorr_ref"] == r["cicp_plugin"]["ncorr_mix"]
+    # the gravity estimator class: CPU loop + GPU estimator == GPU loop; no roll / pitch
+    assert r["gravity"]["dT"] < 1e-6 and abs(r["gravity"]["ncorr_mix"] - r["gravity"]["ncorr_gpu"]) <= 2
+    assert r["gravity"]["roll_pitch"] < 1e-12
+    # A1: ComputeRMSE on the GPU vs the reference's (summation order differs)
+    assert abs(r["rmse"]["ref"] - r["rmse"]["gpu"]) < 1e-12 * max(1.0, r["rmse"]["ref"]) and r["rmse"]["empty"] == 0
+    assert r["rmse"]["ref"] > 0
+    # per-source normals decision in a mixed point-to-plane batch
+    m = r["mixed_normals"]
+    assert m["with_dT"] == 0 and m["with2_dT"] == 0 and m["with_ncorr"] > 1000
+    assert m["bare_dT"] == 0 and m["bare_fitness"] == 0 and m["empty_dT"] == 0
     assert r["errors"]["bad_distance_dT"] == 0 and r["errors"]["no_normals_dT"] == 0
     assert r["errors"]["no_normals_fitness"] == 0
     assert r["voxel"]["n_ref"] == r["voxel"]["n_gpu"] and r["voxel"]["dsum"] < 1e-6

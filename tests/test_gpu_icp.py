@@ -357,3 +357,36 @@ def test_exact_ties_through_the_cached_path(vb, scene):
             assert np.array_equal(full, idx), (it, b, int((full != idx).sum()))
             assert (idx[idx >= 0] < 40000).all()      # ties went to the first copy
         T = np.stack([r.transformation_ for r in got])
+
+
+def test_compute_rmse(vb, oracle, scene):
+    """A1: cicp::TransformationEstimationPointToPoint4DoF::ComputeRMSE (src/constrained_ICP.cpp:13-23) on the GPU."""
+    tgt = scene["scene_xyz"]
+    T0 = scene["T_init"][2]
+    src = scene["sources"][2][0] @ T0[:3, :3].T + T0[:3, 3]
+    oi, _ = oracle.Index(tgt, 0.075).knn1(src, 0.075)
+    corr = np.stack([np.nonzero(oi >= 0)[0], oi[oi >= 0]], 1).astype(np.int32)
+    want = np.sqrt(((src[corr[:, 0]] - tgt[corr[:, 1]]) ** 2).sum(1).sum() / len(corr))
+    got = vb.reg.ComputeRMSE(src, tgt, corr)
+    assert abs(got - want) < 1e-14 and got > 0
+    assert vb.reg.ComputeRMSE(src, tgt, np.zeros((0, 2), np.int32)) == 0.0
+
+
+@pytest.mark.parametrize("name", ["p2p", "p2plane", "gravity"])
+def test_estimator_device_resident(vb, oracle, scene, name):
+    """vb200_estimate_device: clouds and the correspondence list already on the GPU, rows gathered by the kernel."""
+    torch = pytest.importorskip("torch")
+    est, okind = est_of(vb, oracle, name)
+    tgt, tn = scene["scene_xyz"], scene["scene_nrm"]
+    T0 = scene["T_init"][1]
+    src = scene["sources"][1][0] @ T0[:3, :3].T + T0[:3, 3]
+    oi, _ = oracle.Index(tgt, 0.075).knn1(src, 0.075)
+    corr = np.stack([np.nonzero(oi >= 0)[0], oi[oi >= 0]], 1).astype(np.int32)
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (src, tgt, tn, corr)]
+    torch.cuda.synchronize()
+    Tg = vb.reg.ComputeTransformationDevice(est, dev[0].data_ptr(), len(src), dev[1].data_ptr(), dev[2].data_ptr(),
+                                            len(tgt), dev[3].data_ptr(), len(corr))
+    To = oracle.estimate(src, tgt, corr, okind, tgt_nrm=tn, gravity=(0, 1, 0))
+    assert np.allclose(Tg, To, atol=1e-10)
+    Th = vb.reg.ComputeTransformation(est, vb.reg.PointCloud(src), vb.reg.PointCloud(tgt, tn), corr)
+    assert np.allclose(Tg, Th, atol=1e-12)

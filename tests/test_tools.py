@@ -72,7 +72,8 @@ def test_render_depth_tool_outputs(vb, oracle, tmp_path):
     oz, od = oracle.render_depth(V, F, np.asarray(model, np.float32).T.reshape(-1),
                                  oracle.view(np.eye(4, dtype=np.float32).reshape(-1)), P, 480, 640)
     assert (depth == od).all()
-    assert ((mask == 255) == (oz < oracle.ZMAX24)).all() and (mask == 255).sum() > 10000
+    # reference polarity: background 255 (the GL clear colour, render/renderer.cpp:411-422), covered pixels 0
+    assert ((mask == 0) == (oz < oracle.ZMAX24)).all() and (mask == 0).sum() > 10000
     # saving disabled: nothing written
     (tmp_path / "o2").mkdir()
     cfg2 = dict(cfg, save=False, mesh=str(tmp_path / "chair.obj"))

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("VISMA_B200_LIB") or os.path.join(_HERE, "libvisma_b20
 OK = 0
 ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_NORMALS, ERR_DISTANCE = -1, -2, -3, -4, -5, -6
 EST_P2P, EST_P2PLANE, EST_P2PLANE_GRAVITY = 0, 1, 2
+OPT_NN_CACHE, OPT_SPLIT_TIMING = 1, 2
 
 # every symbol include/visma_b200.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
@@ -20,8 +21,9 @@ SYMBOLS = [
     "vb200_scene_create", "vb200_scene_destroy", "vb200_scene_size", "vb200_scene_stream",
     "vb200_scene_sync", "vb200_knn1", "vb200_knn1_device", "vb200_knn1_bruteforce", "vb200_knn1_bruteforce_device", "vb200_icp_run", "vb200_batch_create",
     "vb200_batch_destroy", "vb200_batch_set_problems", "vb200_batch_run", "vb200_batch_results",
-    "vb200_batch_corr", "vb200_batch_launches", "vb200_batch_iterate", "vb200_batch_last_kernel_ms", "vb200_batch_pass",
-    "vb200_batch_set_totals_buffer", "vb200_batch_totals", "vb200_batch_solve", "vb200_estimate", "vb200_register_model_to_scene",
+    "vb200_batch_corr", "vb200_batch_launches", "vb200_batch_iterate", "vb200_batch_set_option", "vb200_batch_last_kernel_ms", "vb200_batch_pass",
+    "vb200_batch_set_totals_buffer", "vb200_batch_totals", "vb200_batch_solve", "vb200_estimate", "vb200_estimate_device", "vb200_rmse",
+    "vb200_register_model_to_scene",
     "vb200_render_depth_batch", "vb200_render_depth_batch_ex", "vb200_render_edge_mask_batch", "vb200_voxel_downsample", "vb200_sample_mesh",
 ]
 
@@ -81,6 +83,7 @@ def lib():
     L.vb200_batch_launches.restype = C.c_int64
     L.vb200_batch_launches.argtypes = [vp]
     L.vb200_batch_iterate.argtypes = [vp, C.c_int, dp, C.c_double, C.c_int]
+    L.vb200_batch_set_option.argtypes = [vp, C.c_int, C.c_int]
     L.vb200_batch_last_kernel_ms.argtypes = [vp, fp, fp]
     L.vb200_batch_pass.argtypes = [vp, C.c_int, C.c_double]
     L.vb200_batch_set_totals_buffer.argtypes = [vp, vp]
@@ -88,6 +91,8 @@ def lib():
     L.vb200_batch_totals.argtypes = [vp]
     L.vb200_batch_solve.argtypes = [vp, C.c_int, dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, i64p]
     L.vb200_estimate.argtypes = [dp, C.c_int64, dp, dp, C.c_int64, ip, C.c_int64, C.c_int, dp, C.c_int, dp]
+    L.vb200_estimate_device.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, C.c_int, dp, C.c_int, vp, dp]
+    L.vb200_rmse.argtypes = [dp, C.c_int64, dp, C.c_int64, ip, C.c_int64, C.c_int, dp]
     L.vb200_register_model_to_scene.argtypes = [vp, dp, dp, C.c_int64, C.c_int, C.c_double, C.c_int, dp, ip, ip]
     L.vb200_render_depth_batch.argtypes = [fp, i64p, ip, i64p, C.c_int32, fp, fp, C.c_float, C.c_float,
                                            C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,

@@ -42,23 +42,15 @@ struct GridParams {
     float band_a, band_b, band_rel;
 };
 
-// Doubles between consecutive scene points in `xyz` (and in `nrm`).  -DVB_XYZN interleaves the two arrays —
-// point and normal of a scene point in one 48-byte record, `nrm` = `xyz` + 3 — so that a matched row of the
-// point-to-plane pass costs exactly two 32-byte sectors instead of three on average (24-byte records straddle
-// a sector boundary half the time).  Off by default: written after the round's GPU time was spent.
-#ifdef VB_XYZN
-constexpr int kPtStride = 6;
-#else
-constexpr int kPtStride = 3;
-#endif
+constexpr int kPtStride = 3;  // doubles between consecutive scene points in `xyz` and in `nrm`
 
 struct GridDev {
     GridParams p;
     const CoarseCell *coarse;
     const int *fstart;
     const float4 *hi;
-    const double *xyz;  // kPtStride doubles per point
-    const double *nrm;  // nullable; kPtStride doubles per point (VB_XYZN: xyz + 3)
+    const double *xyz;  // 3 doubles per point
+    const double *nrm;  // nullable; 3 doubles per point
     const int *orig;
     int64_t n;
 };
@@ -538,9 +530,13 @@ constexpr float kLaneProbeRho = VB_LANE_PROBE_RHO_PCT * 0.01f;  // first reach o
 #endif
 constexpr float kLaneBigRho = VB_BIG_RHO_PCT * 0.01f;  // a reach beyond this counts towards sending the warp to the shared walk
 constexpr unsigned kRunLenBits = 12, kRunLenMask = (1u << kRunLenBits) - 1u;
+#ifndef VB_NB_WINDOW
+#define VB_NB_WINDOW 2
+#endif
+constexpr int kNbWindow = VB_NB_WINDOW;  // previous matches of the lanes within +-this many give the search its bound
 
 #ifdef VB_STATS
-__device__ unsigned long long g_stats[16];
+__device__ unsigned long long g_stats[24];
 #define VB_STAT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
 #else
 #define VB_STAT(i, v) ((void)0)
@@ -552,18 +548,25 @@ __device__ __forceinline__ float widen(float thr, float slack, float cap) {
     return fmaxf(thr, fminf(s * s, cap));
 }
 
+#ifndef VB_LANE_MAX_NEAR
+#define VB_LANE_MAX_NEAR 8
+#endif
+constexpr int kLaneMaxNear = VB_LANE_MAX_NEAR;
+
 template <int TPB>
 struct LaneRuns {  // one column per thread: conflict-free whatever row each lane is at
     int s0[kLaneMaxRuns][TPB];
-    unsigned w[kLaneMaxRuns][TPB];  // gap2 (f32, low 12 mantissa bits dropped = rounded down) | run length
+    unsigned w[kLaneMaxRuns][TPB];  // drop threshold h (f32, low 12 mantissa bits dropped = rounded down) | run length
+    int near[kLaneMaxNear][TPB];    // settling searches: positions of the candidates nearer than the listing threshold
 };
 
 // scan this lane's listed runs; `bound` = f32 distance of a real candidate (or >= r2_ub): cells beyond its reach
-// cannot matter
-template <int TPB>
-__device__ __forceinline__ int scan_runs(const GridDev &G, const QueryCtx &c, int nruns, float bound, float r2_ub,
-                                         float slack, float cap, const LaneRuns<TPB> &L, Screen &r) {
-    const GridParams &g = G.p;
+// cannot matter.  A run carries h, computed when it was listed: while min(bound, best so far) < h the run lies
+// beyond the (widened) reach of the best so far and is dropped (see list_runs_union) — one compare per run.
+// SET: the positions of the candidates with d < near_thr are noted in the lane's column (nnear counts them all).
+template <int TPB, bool SET>
+__device__ __forceinline__ int scan_runs(const GridDev &G, const QueryCtx &c, int nruns, float bound, LaneRuns<TPB> &L,
+                                         Screen &r, float near_thr, int &nnear) {
     const float4 *__restrict__ hi = G.hi;
     const int tid = threadIdx.x & (TPB - 1);
     int ri = 0, s = 0, e = 0;
@@ -575,9 +578,7 @@ __device__ __forceinline__ int scan_runs(const GridDev &G, const QueryCtx &c, in
             s = L.s0[ri][tid];
             e = s + (int)(w & kRunLenMask);
             ++ri;
-            // a listed run is dropped only when it lies beyond the (widened) reach of the best so far: every
-            // cell within widen(reach_of(final best)) is therefore scanned (nn_search_hybrid's `cover`)
-            if (__uint_as_float(w & ~kRunLenMask) > widen(reach_of(g, fminf(bound, r.best), r2_ub), slack, cap)) e = s;
+            if (fminf(bound, r.best) < __uint_as_float(w & ~kRunLenMask)) e = s;
             continue;
         }
         // two candidates per step; the second is masked out when the run has one left
@@ -587,6 +588,10 @@ __device__ __forceinline__ int scan_runs(const GridDev &G, const QueryCtx &c, in
         const float bx = c.qx - tb.x, by = c.qy - tb.y, bz = c.qz - tb.z;
         const float da = fmaf(az, az, fmaf(ay, ay, ax * ax));
         const float db = two ? fmaf(bz, bz, fmaf(by, by, bx * bx)) : 3.0e38f;
+        if (SET) {
+            if (da < near_thr) { if (nnear < kLaneMaxNear) L.near[nnear][tid] = s; ++nnear; }
+            if (db < near_thr) { if (nnear < kLaneMaxNear) L.near[nnear][tid] = s + 1; ++nnear; }
+        }
         const float lo = fminf(da, db), hi2 = fmaxf(da, db);
         const int slo = db < da ? s + 1 : s;
         const bool lt = lo < r.best;
@@ -599,51 +604,49 @@ __device__ __forceinline__ int scan_runs(const GridDev &G, const QueryCtx &c, in
     return steps;
 }
 
-// The three smallest f32 distances among a lane's listed runs and the positions of the first two: a second
-// look at the same candidates, taken only by the rare lanes whose winner and runner-up are too close for a
-// single cached neighbour (see nn_search_hybrid).  Runs beyond `cut` are skipped, as the first scan did.
-struct Top3 {
-    float d0, d1, d2;
-    int s0, s1;
+// The five smallest f32 distances among the candidates a settling search noted (scan_runs<SET>) and the positions
+// of the first four: the lane's candidate SET (see nn_search_hybrid).
+struct Top5 {
+    float e[5];
+    int s[4];
 };
 
 template <int TPB>
-__device__ __forceinline__ Top3 top3_of_runs(const GridDev &G, const QueryCtx &c, int nruns, float cut,
-                                             const LaneRuns<TPB> &L) {
+__device__ __forceinline__ Top5 top5_of_near(const GridDev &G, const QueryCtx &c, int nnear, const LaneRuns<TPB> &L) {
     const int tid = threadIdx.x & (TPB - 1);
-    Top3 t;
-    t.d0 = t.d1 = t.d2 = 3.0e38f;
-    t.s0 = t.s1 = -1;
-    for (int ri = 0; ri < nruns; ++ri) {
-        const unsigned w = L.w[ri][tid];
-        if (__uint_as_float(w & ~kRunLenMask) > cut) continue;
-        int s = L.s0[ri][tid];
-        const int e = s + (int)(w & kRunLenMask);
-        for (; s < e; ++s) {
-            const float4 p = __ldg(G.hi + s);
-            const float dx = c.qx - p.x, dy = c.qy - p.y, dz = c.qz - p.z;
-            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            if (d < t.d0) {
-                t.d2 = t.d1; t.d1 = t.d0; t.s1 = t.s0;
-                t.d0 = d; t.s0 = s;
-            } else if (d < t.d1) {
-                t.d2 = t.d1;
-                t.d1 = d; t.s1 = s;
-            } else if (d < t.d2) {
-                t.d2 = d;
-            }
-        }
+    float e0 = 3.0e38f, e1 = 3.0e38f, e2 = 3.0e38f, e3 = 3.0e38f, e4 = 3.0e38f;
+    int s0 = -1, s1 = -1, s2 = -1, s3 = -1;
+    for (int i = 0; i < nnear; ++i) {
+        const int s = L.near[i][tid];
+        const float4 p = __ldg(G.hi + s);
+        const float dx = c.qx - p.x, dy = c.qy - p.y, dz = c.qz - p.z;
+        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        // sorted insertion (strict: equal distances keep their scan order)
+        const bool l4 = d < e4, l3 = d < e3, l2 = d < e2, l1 = d < e1, l0 = d < e0;
+        e4 = l3 ? e3 : (l4 ? d : e4);
+        e3 = l2 ? e2 : (l3 ? d : e3); s3 = l2 ? s2 : (l3 ? s : s3);
+        e2 = l1 ? e1 : (l2 ? d : e2); s2 = l1 ? s1 : (l2 ? s : s2);
+        e1 = l0 ? e0 : (l1 ? d : e1); s1 = l0 ? s0 : (l1 ? s : s1);
+        e0 = l0 ? d : e0;             s0 = l0 ? s : s0;
     }
+    Top5 t;
+    t.e[0] = e0; t.e[1] = e1; t.e[2] = e2; t.e[3] = e3; t.e[4] = e4;
+    t.s[0] = s0; t.s[1] = s1; t.s[2] = s2; t.s[3] = s3;
     return t;
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// list the occupied fine cells with done < gap2 <= thr (squared distance to the query) as runs, in ONE flat
-// loop over the cells of the query's box (nested loops with per-lane trip counts serialise: measured 30 passes of the inner body per warp
-// for 2.5 runs per lane).  Returns the number of runs, or kLaneMaxRuns + 1 when the lane must fall back.
+// list the occupied fine cells with done < gap2 <= thr (squared distance to the query, deflated) as runs, in ONE
+// flat loop over the cells of the query's box (nested loops with per-lane trip counts serialise: measured 30 passes
+// of the inner body per warp for 2.5 runs per lane; a warp-cooperative walk over the UNION of the lanes' boxes was
+// measured twice as slow as this: the union of 32 neighbouring boxes holds ~5x the occupied cells of one box and
+// every lane pays for each).  Returns the number of runs, or kLaneMaxRuns + 1 when the lane must fall back.
+// Each listed run gets h: while min(bound, best so far) < h the scan may drop the run.  With W(b) =
+// widen(reach_of(b), slack) the scan must keep every run with gap2 <= W(final best); h = g' - 2 bnd(g') with
+// sqrt(g') = sqrt(gap2) - slack satisfies b < h  =>  (sqrt(reach_of(b)) + slack)^2 < gap2  =>  W(b) < gap2.
 template <int TPB>
-__device__ __forceinline__ int list_runs(const GridDev &G, const QueryCtx &c, float thr, float done,
+__device__ __forceinline__ int list_runs(const GridDev &G, const QueryCtx &c, float thr, float done, float slack,
                                          LaneRuns<TPB> &L) {
     const GridParams &g = G.p;
     const int tid = threadIdx.x & (TPB - 1);
@@ -679,8 +682,12 @@ __device__ __forceinline__ int list_runs(const GridDev &G, const QueryCtx &c, fl
                     z = z1; y = y1; x = x1;
                 } else {
                     prefetch_l1(G.hi + s0);
+                    const float sg = fmaxf(sqrtf(gap2) - slack, 0.0f) * 0.999999f;
+                    const float gp = sg * sg;
+                    const float bnd = fmaf(g.band_a * 1.001f, sqrtf(gp), fmaf(g.band_rel * 1.001f, gp, g.band_b * 1.001f));
+                    const float h = fmaxf(fmaf(-2.0f, bnd, gp), 0.0f);
                     L.s0[n][tid] = s0;
-                    L.w[n][tid] = (__float_as_uint(gap2) & ~kRunLenMask) | (unsigned)(s1 - s0);
+                    L.w[n][tid] = (__float_as_uint(h) & ~kRunLenMask) | (unsigned)(s1 - s0);
                     ++n;
                 }
             }
@@ -699,21 +706,27 @@ __device__ __forceinline__ int list_runs(const GridDev &G, const QueryCtx &c, fl
     return n;
 }
 
+// What a search proved about every target point it did NOT return, for the caller's cached-neighbour tests
+// (k_pass_a: Greenspan & Godin's test for ICP, made exact).  All bounds are on TRUE squared distances from the
+// query position of this search.
+struct SearchProof {
+    float sec1;     // > 0: every target point other than the returned one is at least this far; <= 0: nothing known
+    float secK;     // > 0: every target point other than the returned one and others[] is at least this far
+    int others[3];  // the rest of the candidate set (sorted positions, -1 = unused), nearest first
+};
+
 // All 32 lanes of the warp must call this together.  `prior` = sorted position of a target point believed to
 // be close to the query (or -1): only ever used as an upper bound, never as an answer.
 //
-// `slack` (metric, >= 0) widens every lane-private search beyond what the answer needs, and *sec_out (nullable)
-// receives what the search proved about everything else: sec > 0 = a lower bound of the TRUE squared distance
-// from the query to every target point other than the returned one; sec < 0 with *second_out >= 0 = the same
-// bound (-sec) for every point other than the returned one AND the runner-up *second_out; sec == -1 with no
-// runner-up = nothing.  The caller keeps it with the query position and can later prove, by the triangle
-// inequality, that the answer is unchanged after a small move (k_pass: Greenspan & Godin's cached-neighbour
-// test for ICP).
+// `slack` (metric, >= 0) widens every lane-private search beyond what the answer needs; with `want_set` a lane
+// that completed its search in one lane-private round takes a second look at its candidates and returns the
+// four nearest as a SET (proof->others) with a bound on everything outside it: after a small move the caller
+// can then settle the point among four candidates instead of searching again.
 template <int TPB>
 __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, const QueryCtx &c, double qx, double qy,
                                                 double qz, double r2, float r2_ub, int prior, LaneRuns<TPB> &L,
-                                                double *d2_out, float slack = 0.0f, float *sec_out = nullptr,
-                                                int coop_lanes = 32, int *second_out = nullptr) {
+                                                double *d2_out, float slack = 0.0f, SearchProof *proof = nullptr,
+                                                int coop_lanes = 32, bool want_set = false) {
     const unsigned FULL = 0xffffffffu;
     static_assert((TPB & (TPB - 1)) == 0, "TPB must be a power of two");
     const GridParams &g = G.p;
@@ -725,39 +738,21 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
     float thr = (kLaneProbeRho * g.fine) * (kLaneProbeRho * g.fine);  // no bound yet: probe the nearest cells
     int mode = valid ? kScan : kDone;
     {
-        // Bound = distance to the nearest of the WARP's previous matches, not just the lane's own.  Under a rigid
-        // move the points of a patch slide together: a point that has moved a centimetre along the surface is
-        // now nearest to what was its lane neighbour's match, and its own old match would give twice the reach
-        // (eight times the cells).  The lanes of a warp are spatial neighbours, so their 32 old matches are the
-        // scene points around the query — 32 candidate bounds for ~10 instructions each.
+        // Bound = distance to the nearest of the previous matches of this lane and of its neighbours in the warp.
+        // Under a rigid move the points of a patch slide together: a point that has moved a centimetre along the
+        // surface is now nearest to what was its lane neighbour's match, and its own old match would give twice
+        // the reach (eight times the cells).  The lanes are in spatial order, so the nearest old matches are
+        // mostly the adjacent lanes': +-kNbWindow lanes (checking all 32 measured no faster than checking none).
         float4 t = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.0f);
         if (valid && prior >= 0) t = __ldg(G.hi + prior);
-#if defined(VB_NB_WINDOW)
-        // dev variant: only the previous matches of the lanes within +-VB_NB_WINDOW of this one (the lanes are in
-        // spatial order, so the nearest old matches are mostly the adjacent lanes'): 2W+1 checks instead of up
-        // to 32.  Any real scene point gives a valid bound; lanes without a match hold the far-away sentinel.
         float nb = 3.0e38f;
 #pragma unroll
-        for (int o = -(VB_NB_WINDOW); o <= (VB_NB_WINDOW); ++o) {
+        for (int o = -kNbWindow; o <= kNbWindow; ++o) {
             const int j = ((threadIdx.x & 31) + o) & 31;
             const float dx = c.qx - __shfl_sync(FULL, t.x, j), dy = c.qy - __shfl_sync(FULL, t.y, j),
                         dz = c.qz - __shfl_sync(FULL, t.z, j);
             nb = fminf(nb, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
         }
-#elif !defined(VB_NO_NEIGHBOUR_BOUNDS)
-        unsigned have = __ballot_sync(FULL, valid && prior >= 0);
-        float nb = 3.0e38f;
-        while (have) {
-            const int j = __ffs(have) - 1;
-            have &= have - 1u;
-            const float dx = c.qx - __shfl_sync(FULL, t.x, j), dy = c.qy - __shfl_sync(FULL, t.y, j),
-                        dz = c.qz - __shfl_sync(FULL, t.z, j);
-            nb = fminf(nb, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-        }
-#else
-        const float dx = c.qx - t.x, dy = c.qy - t.y, dz = c.qz - t.z;
-        const float nb = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-#endif
         if (valid && nb < r2_ub) {
             bound = nb;
             thr = reach_of(g, bound, r2_ub);
@@ -776,21 +771,23 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
     VB_STAT(1, bound < r2_ub);
     if ((threadIdx.x & 31) == 0) VB_STAT(11, 1);
     float done = -1.0f;  // every cell with gap2 <= done has been scanned
-    int nscans = 0, last_nruns = 0;  // rounds this lane scanned, and the length of its latest list
+    int nscans = 0, nnear = 0;  // rounds this lane scanned; candidates its latest scan found below the listing threshold
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
-        int nruns = 0, steps = 0;
+        if (!__any_sync(FULL, mode == kScan)) break;
+        int steps = 0;
         if (mode == kScan) {
-            nruns = list_runs<TPB>(G, c, thr, done, L);
+            const int nruns = list_runs<TPB>(G, c, thr, done, slack, L);
             if (nruns > kLaneMaxRuns) {
                 mode = kCoop;
                 VB_STAT(5, 1);
             } else {
                 VB_STAT(7, nruns);
-                steps = scan_runs<TPB>(G, c, nruns, bound, r2_ub, slack, max_reach2, L, r);
+                nnear = 0;
+                steps = want_set ? scan_runs<TPB, true>(G, c, nruns, bound, L, r, thr, nnear)
+                                 : scan_runs<TPB, false>(G, c, nruns, bound, L, r, thr, nnear);
                 done = thr;
                 ++nscans;
-                last_nruns = nruns;
                 if (r.bs >= 0) {
                     // complete once the reach of the final best lies inside what has been scanned
                     const float need = reach_of(g, fminf(bound, r.best), r2_ub);
@@ -814,7 +811,6 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
 #else
         (void)steps;
 #endif
-        if (!__any_sync(FULL, mode == kScan)) break;
     }
     if (mode == kScan) mode = kCoop;  // still open after two rounds
     const bool lane_private = mode == kDone && valid;  // every cell with gap2 <= done was scanned by this lane
@@ -826,8 +822,10 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
         if (mode == kCoop) r = rc;
     }
     *d2_out = 0.0;
-    if (sec_out) *sec_out = -1.0f;
-    if (second_out) *second_out = -1;
+    if (proof) {
+        proof->sec1 = -1.0f; proof->secK = -1.0f;
+        proof->others[0] = proof->others[1] = proof->others[2] = -1;
+    }
     if (!valid || r.bs < 0) return -1;
     // ---- the decision, in double
     const float bb = band(g, r.best);
@@ -837,40 +835,58 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
     const float reach = reach_of(g, fminf(bound, r.best), r2_ub);
     const float wide = widen(reach, slack, max_reach2);
     const float cover = lane_private ? fminf(done, wide) : reach;
-    // scanned points other than r.bs: d32 >= r.second, hence true d2 >= r.second - band(r.second)
-    const float m1 = fminf(r.second, cover);
-    const float sec1 = m1 - band(g, m1);
-    if (sec_out && lane_private && nscans == 1) {
-        // Would the answer hold as ONE cached neighbour (k_pass_a's test, before any move)?  If the runner-up is
-        // that close — or the f32 distances cannot even tell the two apart — keep BOTH: a second look at this
-        // lane's candidates finds the runner-up's position and the third-smallest distance, the winner between
-        // the two is taken in double, and the caller caches the pair with a bound on everything else.
-        // (only when the runner-up itself is what limits the bound: a lane whose bound is its scan radius —
-        // every search of an alignment's first iterations — gains nothing from a second candidate)
-        const bool lone = unique && sqrtf(r.best + bb) * 1.000001f + g.band_a < sqrtf(fmaxf(sec1, 0.0f)) * 0.999999f;
-        if (!lone && r.second < cover) {
-            const Top3 t = top3_of_runs<TPB>(G, c, last_nruns, wide, L);
-            const float m3 = fminf(t.d2, cover);
-            const float sec3 = m3 - band(g, m3);  // true d2 of every point other than the two is above this
-            if (t.s1 >= 0 && sec3 > t.d0 + band(g, t.d0)) {
-                const double da = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)t.s0);
-                const double db = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)t.s1);
-                // exact ties break to the lowest ORIGINAL index (the documented rule, as nn_exact_rescan)
-                const bool first = da < db || (da == db && __ldg(G.orig + t.s0) < __ldg(G.orig + t.s1));
-                const double dw = first ? da : db;
-                if (!(dw < r2)) return -1;
-                *d2_out = dw;
-                *sec_out = -sec3;  // negative: a two-candidate entry
-                if (second_out) *second_out = first ? t.s1 : t.s0;
-                return first ? t.s0 : t.s1;
+    VB_STAT(20, want_set && lane_private && nscans == 1);
+    VB_STAT(21, want_set && lane_private && nscans == 1 && nnear > kLaneMaxNear);
+    VB_STAT(22, want_set && lane_private && nscans == 1 && nnear < 2);
+    VB_STAT(23, want_set && valid && !(lane_private && nscans == 1));
+    if (proof && want_set && lane_private && nscans == 1 && nnear >= 2 && nnear <= kLaneMaxNear) {
+        // The (up to) four nearest of the candidates the scan found below its listing threshold, as a set.
+        // Scanned points outside it have d32 >= min(e[4], threshold), hence true d2 >= that minus its band
+        // (the threshold is `done` >= cover); unscanned ones lie beyond `cover`.
+        const Top5 t = top5_of_near<TPB>(G, c, nnear, L);
+        VB_STAT(16, 1);
+        const float m5 = fminf(t.e[4], cover);
+        const float secK = m5 - band(g, m5);
+        const float ub0 = t.e[0] + band(g, t.e[0]);  // the f32-nearest candidate is truly no farther than this
+        if (t.s[1] >= 0 && secK > ub0) {
+            // the true nearest is in the set; contenders are the members that could be nearer than t.s[0].
+            // Exact ties break to the lowest ORIGINAL index (the documented rule, as nn_exact_rescan).
+            int w = 0;
+            double dw = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)t.s[0]);
+#pragma unroll
+            for (int j = 1; j < 4; j++) {
+                if (t.s[j] >= 0 && t.e[j] - band(g, t.e[j]) <= ub0) {
+                    const double dj = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)t.s[j]);
+                    if (dj < dw || (dj == dw && __ldg(G.orig + t.s[j]) < __ldg(G.orig + t.s[w]))) { w = j; dw = dj; }
+                }
             }
+            if (!(dw < r2)) return -1;
+            *d2_out = dw;
+            float o1 = 3.0e38f;  // lower bound of the true d2 of the set's other members
+            int k = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j != w) {
+                    if (t.s[j] >= 0) o1 = fminf(o1, t.e[j] - band(g, t.e[j]));
+                    proof->others[k++] = t.s[j];
+                }
+            }
+            proof->secK = secK;
+            proof->sec1 = fminf(secK, o1);
+            VB_STAT(17, 1);
+            VB_STAT(18, t.e[4] < cover);  // the set's bound is the fifth candidate, not the scanned radius
+            return t.s[w];
         }
     }
     if (unique) {
         const double d = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)r.bs);
         if (!(d < r2)) return -1;
         *d2_out = d;
-        if (sec_out) *sec_out = sec1;
+        if (proof) {
+            // scanned points other than r.bs: d32 >= r.second, hence true d2 >= r.second - band(r.second)
+            const float m1 = fminf(r.second, cover);
+            proof->sec1 = m1 - band(g, m1);
+        }
         return r.bs;
     }
     return nn_exact_rescan(G, c, qx, qy, qz, r2, fminf(r.best + 2.0f * bb, r2_ub), d2_out);

@@ -33,16 +33,11 @@ namespace vb {
 
 namespace {
 
-// Part B of the pass runs over a worklist of the blocks that listed anything (k_pass_b_wl) unless the older
-// one-block-per-(block, warp) launch is asked for (-DVB_PB_PER_BLOCK; the fused iteration tail needs it too).
-#if !defined(VB_PB_PER_BLOCK) && !defined(VB_FUSE_SOLVE) && !defined(VB_PB_WORKLIST)
-#define VB_PB_WORKLIST
-#endif
 #ifndef VB_PASS_TPB
 #define VB_PASS_TPB 128
 #endif
 #ifndef VB_PASS_MINBLOCKS
-#define VB_PASS_MINBLOCKS (768 / VB_PASS_TPB)  // 24 resident warps per SM -> 80 registers per thread
+#define VB_PASS_MINBLOCKS (768 / VB_PASS_TPB)  // part B: 24 resident warps per SM -> 80 registers per thread
 #endif
 constexpr int kPassTpb = VB_PASS_TPB;
 constexpr int kPassWarps = kPassTpb / 32;  // every warp writes its own partial: no block-level barrier
@@ -56,20 +51,26 @@ constexpr int kBuckets = 32768;                   // spatial buckets per source 
 
 // accumulator slots, MODE 1 (point-to-plane): 0..20 JTJ upper triangle row-major, 21..26 JTr
 // MODE 0 (point-to-point): 0..2 sum s', 3..5 sum d', 6..14 sum d' s'^T (row-major), 15 sum |s'|^2
-// both: 30 = sum d2 (exact NN distances), 31 = count
-constexpr int kSlotD2 = 30, kSlotCount = 31;
+// both: 28 = sum |s - d|^2 (estimator plug-in only), 30 = sum d2 (exact NN distances), 31 = count
+constexpr int kSlotRes2 = 28, kSlotD2 = 30, kSlotCount = 31;
 
 struct ProbState {
     double T[16];
     double fitness, rmse, prev_fitness, prev_rmse;
-    int ncorr, iters, done, pad;
+    int ncorr, iters, done;
+    // How far ANY point of the problem can have moved, as an upper bound accumulated over the estimator updates
+    // since set_problems (k_solve adds each update's bound, rounded up): the difference between two readings
+    // bounds the move of every point between them, which is all the cached-neighbour tests need to know.
+    float cum;
+    float last_move;  // the latest update's share (huge before the first update)
+    int pad;
 };
 
 struct BlockTask {
     int prob;       // problem index
     int src_begin;  // first source point (global sorted position)
     int count;      // points in this block's chunk
-    int corr_begin; // where this chunk's matches go in corr_j
+    int corr_begin; // where this chunk's records start
 };
 
 struct ProbDesc {
@@ -78,35 +79,62 @@ struct ProbDesc {
     int blk_begin, blk_count;
     int src_begin;
     int corr_begin;
+    double ctr[3];  // centre of the cloud's bounding box (its own frame) ...
+    double rad;     // ... and the largest distance of a point from it
+};
+
+// What a source point remembers between passes, per (problem, point).  `hot` is all a settled pass reads:
+//   c0    the point's match as a SORTED scene position (-1 none): the correspondence list, and the next search's bound;
+//   lim1  sqrt(sec1) + cum at the time of the proof, rounded down, where sec1 bounds (from below) the true squared
+//         distance from the point's position THEN to every scene point other than c0.  While
+//         |q_now - c0| + cum_now < lim1 the triangle inequality proves c0 is still the unique nearest neighbour.
+//         NaN (memset 0xff) or 0 = knows nothing.
+// `cold` is read only when that test fails: three more candidates and limK, the same bound for every scene point
+// outside {c0, c1, c2, c3}: while min_j |q_now - c_j| + cum_now < limK the nearest neighbour is one of the four and
+// is settled among them in double.
+struct __align__(8) HotRec {
+    int c0;
+    float lim1;
+};
+struct __align__(16) ColdRec {
+    int c1, c2, c3;
+    float limK;
 };
 
 struct PassParams {
-    double r2;      // (double)(float)(max_dist^2)  (KDTreeFlann.cpp:185)
-    float r2_ub;    // f32 upper bound of r2 including the screening band
-    float slack;    // how far beyond the answer's reach a search looks, so that its result survives small moves
-    float pos_err;  // bound on the error of a distance between two centred-f32 query positions
-    int use_cache;  // 0: every point is searched in every pass (dev knob VB200_NN_CACHE=0: the ablation bench.py reports)
-#ifdef VB_PB_WORKLIST
-    int *work;      // part-A blocks that listed anything in this pass, in order of arrival
-    int *work_ctr;  // [parity][2]: {blocks listed, part-B items handed out}; passes alternate between the two pairs
+    double r2;        // (double)(float)(max_dist^2)  (KDTreeFlann.cpp:185)
+    float r2_ub;      // f32 upper bound of r2 including the screening band
+    float pos_err;    // absolute guard of the cached-neighbour tests (f32 centring of the query, f64 rounding of T p)
+    float slack_lo, slack_hi;  // how far beyond the answer's reach a search of a settling problem looks (metric)
+    float set_move;   // a problem whose latest update moved it by less than this is "settling": its searches keep sets
+    int use_cache;    // 0: every point is searched in every pass (the ablation bench.py reports)
+    int *work;        // part-A blocks that listed anything in this pass, in order of arrival
+    int *work_ctr;    // [parity][2]: {blocks listed, part-B items handed out}; passes alternate between the two pairs
     int parity;
-#endif
 };
-#if defined(VB_PB_WORKLIST) && defined(VB_FUSE_SOLVE)
-#error "the worklist part B has no fused iteration tail"
-#endif
 
-#ifndef VB_SLACK_PCT
-#define VB_SLACK_PCT 8
+#ifndef VB_SLACK_LO_PCT
+#define VB_SLACK_LO_PCT 8
 #endif
-inline PassParams make_pass_params(const GridParams &g, double max_dist) {
+#ifndef VB_SLACK_HI_PCT
+#define VB_SLACK_HI_PCT 30
+#endif
+#ifndef VB_SET_MOVE_PCT
+#define VB_SET_MOVE_PCT 60
+#endif
+#ifndef VB_SLACK_MOVE_PCT
+#define VB_SLACK_MOVE_PCT 50  // an alignment's updates shrink ~3-4x per iteration: everything still to come is < half the last one
+#endif
+inline PassParams make_pass_params(const GridParams &g, double max_dist, bool use_cache) {
     PassParams pp;
+    memset(&pp, 0, sizeof(pp));
     pp.r2 = (double)(float)(max_dist * max_dist);
     pp.r2_ub = r2_upper_bound(g, pp.r2);
-    pp.slack = g.fine * (VB_SLACK_PCT * 0.01f);
-    pp.pos_err = g.band_a;  // band_a = 2 sqrt(3) e with e the per-axis error of such a difference: a 2x margin
-    const char *nc = getenv("VB200_NN_CACHE");
-    pp.use_cache = !(nc && nc[0] == '0');
+    pp.slack_lo = g.fine * (VB_SLACK_LO_PCT * 0.01f);
+    pp.slack_hi = g.fine * (VB_SLACK_HI_PCT * 0.01f);
+    pp.set_move = g.fine * (VB_SET_MOVE_PCT * 0.01f);
+    pp.pos_err = g.band_a;  // band_a = 2 sqrt(3) e with e the per-axis f32 rounding of a centred coordinate
+    pp.use_cache = use_cache ? 1 : 0;
     return pp;
 }
 
@@ -118,8 +146,14 @@ struct SolveParams {
     int *ndone;  // nullable: counts the problems that have finished (lets the host stop enqueueing iterations)
 };
 
+// ---- programmatic dependent launch: the three kernels of an iteration are chained with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's blocks are resident and past their
+// prologue when the previous one drains.  Nothing produced by the previous kernel is touched before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // ---- warp-level vector reduction: 32 slots over 32 lanes in 31 exchange steps (recursive halving).
-// After the call lane L holds the warp total of slot L.  Fixed order => deterministic.
+// After the call lane L holds the warp total of slot L.  Fixed order => deterministic.  (estimator plug-in)
 __device__ __forceinline__ double warp_reduce_slots(double (&v)[kAcc]) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -136,14 +170,15 @@ __device__ __forceinline__ double warp_reduce_slots(double (&v)[kAcc]) {
 }
 
 template <int MODE>
-__device__ __forceinline__ void contributions(bool matched, double d2, const double *vs, const double *vt,
+__device__ __forceinline__ void contributions(bool matched, const double *vs, const double *vt,
                                               const double *nt, const double *cref, double (&v)[kAcc]) {
 #pragma unroll
     for (int j = 0; j < kAcc; j++) v[j] = 0.0;
     if (!matched) return;
+    const double ex = vs[0] - vt[0], ey = vs[1] - vt[1], ez = vs[2] - vt[2];
     if (MODE == 1) {
         // r = (vs - vt).nt ; J = [vs x nt ; nt]  (TransformationEstimation.cpp:87-89)
-        double r = (vs[0] - vt[0]) * nt[0] + (vs[1] - vt[1]) * nt[1] + (vs[2] - vt[2]) * nt[2];
+        double r = ex * nt[0] + ey * nt[1] + ez * nt[2];
         double J[6] = {vs[1] * nt[2] - vs[2] * nt[1], vs[2] * nt[0] - vs[0] * nt[2],
                        vs[0] * nt[1] - vs[1] * nt[0], nt[0], nt[1], nt[2]};
         int k = 0;
@@ -165,7 +200,7 @@ __device__ __forceinline__ void contributions(bool matched, double d2, const dou
             for (int b = 0; b < 3; b++) v[6 + 3 * a + b] = d[a] * s[b];
         v[15] = s[0] * s[0] + s[1] * s[1] + s[2] * s[2];
     }
-    v[kSlotD2] = d2;
+    v[kSlotRes2] = (ex * ex + ey * ey) + ez * ez;  // (s - t).squaredNorm()  (src/constrained_ICP.cpp:19)
     v[kSlotCount] = 1.0;
 }
 
@@ -189,24 +224,16 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-// what a source point remembers from its last search (16 B, same indexing as corr_s): the query position then
-// (centred f32, as QueryCtx) and `sec`, a lower bound of the true squared distance from there to every target
-// point other than its match.  memset 0xff = NaN = "knows nothing".
-struct __align__(16) NNCache {
-    float qx, qy, qz, sec;
-};
-
 // One ICP correspondence pass for every active problem: transform + radius-bounded 1-NN + estimator
 // products + reduction.  grid = one block per kChunk source points of one problem; every warp owns
 // kPtsPerThread batches of 32 consecutive (spatially sorted) points.
 //
-// 1. Cached-neighbour test (Greenspan & Godin 2001, exact): a point whose last search left the bound `sec`
-//    and which has since moved by delta still has the same nearest neighbour b if
-//    |q - b| < sqrt(sec) - delta (triangle inequality, all f32 error bands on the safe side).  Such a point
-//    needs no search at all: its row goes straight into the estimator sums.  Once an alignment settles this
-//    is nearly every point, and the pass becomes a streaming gather/reduce.
-// 2. The points that fail the test are compacted per warp (ballot ranks, deterministic) and searched 32 at a
-//    time with all lanes busy (nn_search_hybrid); each search refreshes the point's cache.
+// 1. Cached-neighbour tests (Greenspan & Godin 2001, made exact; see HotRec): a point whose last search left a
+//    bound on everything but its match (or on everything but a set of four candidates) needs no search while the
+//    problem has moved by less than that bound allows.  Once an alignment settles this is nearly every point, and
+//    the pass becomes a streaming gather/reduce.
+// 2. The points that fail are compacted per warp (ballot ranks, deterministic) and searched 32 at a time with all
+//    lanes busy (k_pass_b_wl, nn_search_hybrid); each search refreshes the point's records.
 // The decision is always taken in double from the exact coordinates: d2 = |q - b|^2 with FLANN's operation
 // order, accepted iff d2 < (double)(float)(r*r).
 //
@@ -215,9 +242,7 @@ struct __align__(16) NNCache {
 // [s' (3), d' (3), 1, 0] with (s', d') = (vs - c, vt - c) — and the warp accumulates the Gram matrix
 // sum_i x_i x_i^T with 8 DMMA instructions per 32 rows: JTJ = D[0..5][0..5], JTr = D[0..5][6]
 // (resp. the umeyama moments sum d' s'^T = D[3..5][0..2], sum s' = D[0..2][6], sum d' = D[3..5][6]).  The
-// accumulator fragment lives in two registers per lane for the whole warp.  (The first version formed 27
-// products per lane and reduced 32 slots with a 31-step shuffle tree: ~280 instructions and 64 live
-// registers per batch.)
+// accumulator fragment lives in two registers per lane for the whole warp.
 template <int MODE>
 struct PassCtx {
     const GridDev &G;
@@ -240,16 +265,9 @@ struct PassCtx {
         const double *t = G.xyz + kPtStride * (int64_t)bs;
         const double vt[3] = {t[0], t[1], t[2]};
         const double d2 = l2_exact(vs[0], vs[1], vs[2], vt);
-        return row_known(bs, vt, d2, vs, r2, x);
-    }
-
-    // the same from a target point already loaded and its exact distance
-    // (nt_loaded: the target normal when the caller has fetched it already, alongside the point)
-    __device__ __forceinline__ bool row_known(int bs, const double (&vt)[3], double d2, const double (&vs)[3], double r2,
-                                              double (&x)[8], const double *nt_loaded = nullptr) {
         if (!(d2 < r2)) return false;
         if (MODE == 1) {
-            const double *nn = nt_loaded ? nt_loaded : G.nrm + kPtStride * (int64_t)bs;
+            const double *nn = G.nrm + kPtStride * (int64_t)bs;
             const double nt[3] = {nn[0], nn[1], nn[2]};
             x[0] = vs[1] * nt[2] - vs[2] * nt[1];
             x[1] = vs[2] * nt[0] - vs[0] * nt[2];
@@ -315,29 +333,56 @@ struct PassCtx {
 #endif
 constexpr int kRowsPerBlock = 1 + kPassWarps;  // partial rows per block: k_pass_a's (block total), then k_pass_b's warps
 
-// ---- pass, part A: every point.  Streaming: transform, cached-neighbour test, and for the points it settles
+// sqrt(x) * (1 - 1e-6) + cum, every step rounded DOWN: the stored side of a cached-neighbour test
+__device__ __forceinline__ float lim_of(float sec, float cum) {
+    if (!(sec > 0.0f)) return 0.0f;
+    return __fadd_rd(__fmul_rd(__fsqrt_rd(sec), 0.999999f), cum);
+}
+// sqrt(d) * (1 + 1e-6) + cum, every step rounded UP: the moving side of the test (d = f32 distance + its band)
+__device__ __forceinline__ float reach_now(float d_ub, float cum_eps) {
+    return __fadd_ru(__fmul_ru(__fsqrt_ru(d_ub), 1.000001f), cum_eps);
+}
+
+// Part A's rare path: the nearest neighbour is known to be one of cand[0..3] (-1 = unused) but their f32
+// distances cannot order them.  Exact distances; ties to the lowest ORIGINAL index (the rule of nn_exact_rescan).
+static __device__ __noinline__ int settle_set_exact(const GridDev &G, double qx, double qy, double qz, int c0, int c1, int c2,
+                                                    int c3) {
+    const int cand[4] = {c0, c1, c2, c3};
+    int w = -1, wo = 0x7fffffff;
+    double dw = 0.0;
+    for (int j = 0; j < 4; j++) {
+        if (cand[j] < 0) continue;
+        const double d = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)cand[j]);
+        const int o = __ldg(G.orig + cand[j]);
+        if (w < 0 || d < dw || (d == dw && o < wo)) { w = j; dw = d; wo = o; }
+    }
+    return w;
+}
+
+// ---- pass, part A: every point.  Streaming: transform, cached-neighbour tests, and for the points they settle
 // the exact decision and the estimator row.  The rest are listed per warp (ballot ranks: deterministic order)
 // for part B.  No search code in here, so the kernel runs at high occupancy: it is a gather/reduce bound by
 // memory latency and bandwidth.
 template <int MODE>
 __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
     GridDev G, const double *__restrict__ src_xyz, const BlockTask *__restrict__ tasks,
-    const ProbState *__restrict__ states, double *__restrict__ partials, int *__restrict__ corr_s,
-    const NNCache *__restrict__ cache, int *__restrict__ second_s, unsigned char *__restrict__ hard_ids,
-    int *__restrict__ hard_cnt, PassParams pp) {
-    const BlockTask task = tasks[blockIdx.x];
+    const ProbState *__restrict__ states, double *__restrict__ partials, HotRec *__restrict__ hot,
+    ColdRec *__restrict__ cold, unsigned char *__restrict__ hard_ids, int *__restrict__ hard_cnt, PassParams pp) {
+    const BlockTask task = tasks[blockIdx.x];  // static since set_problems: safe before the dependency resolves
+    pdl_launch_dependents();
+    pdl_wait();  // the previous iteration's k_solve (T, cum) and part B (records) are complete and visible
     const ProbState *st = states + task.prob;
-#ifdef VB_PB_WORKLIST
     // the counters the NEXT pass will use: idle since the previous pass's part B finished
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         pp.work_ctr[2 * (pp.parity ^ 1)] = 0;
         pp.work_ctr[2 * (pp.parity ^ 1) + 1] = 0;
     }
-#endif
     if (st->done) return;
     __shared__ __align__(16) double rows_sh[kPassWarps][32 * kRowStride];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     PassCtx<MODE> ctx(G, st->T);
+    const float cum = st->cum;
+    const float cum_eps = __fadd_ru(cum, pp.pos_err);
     unsigned char *my_hard = hard_ids + ((int64_t)blockIdx.x * kPassWarps + warp) * (32 * kPtsPerThread);
     int nhard = 0;  // warp-uniform
 #pragma unroll 1
@@ -353,125 +398,79 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
             const bool inside = make_query(G.p, vs[0], vs[1], vs[2], c);
             const int slot = task.corr_begin + local;
             if (!inside) {
-                corr_s[slot] = -1;  // farther than a cell outside the grid: no neighbour within the radius
+                hot[slot].c0 = -1;  // farther than a cell outside the grid: no neighbour within the radius
             } else {
                 hard = true;
-#if defined(VB_PA_NOHI) && !defined(VB_NO_NN_CACHE)
-                // The cached-neighbour test without the f32 screening array: how far the point has moved since
-                // its last search is known from the streamed cache entry alone, and unless that is less than
-                // the entry's bound nothing below can succeed — no gather at all for such a point (every point,
-                // in an alignment's first iterations).  Otherwise the match's exact coordinates are needed
-                // anyway: |q - b| comes from them in double (rounded up to f32: tighter than the screening
-                // distance + band), one level of dependent loads fewer and one 32-byte sector per point less.
-                const int prior = pp.use_cache ? corr_s[slot] : -1;
-                if (prior >= 0) {
-                    const NNCache m = cache[slot];
-                    const float mx = c.qx - m.qx, my = c.qy - m.qy, mz = c.qz - m.qz;
-                    const float mv = sqrtf(fmaf(mz, mz, fmaf(my, my, mx * mx))) * 1.000001f + pp.pos_err;
-                    const float lim = sqrtf(fabsf(m.sec)) * 0.999999f;  // NaN (no cache) compares false
-                    if (mv < lim) {
-                        const double *tp = G.xyz + kPtStride * (int64_t)prior;
-                        const double vt[3] = {tp[0], tp[1], tp[2]};
-                        // (the normal is fetched with the point, not after the test: a point that gets here
-                        // nearly always passes, and the two gathers then overlap)
-                        double nt[3] = {0.0, 0.0, 0.0};
-                        if (MODE == 1 && m.sec >= 0.0f) {
-                            const double *np = G.nrm + kPtStride * (int64_t)prior;
-                            nt[0] = np[0]; nt[1] = np[1]; nt[2] = np[2];
-                        }
-                        const double da = l2_exact(vs[0], vs[1], vs[2], vt);
-                        if (m.sec >= 0.0f) {
-                            // |q - b| (upper bound) + move (upper bound) < distance to anything else then (lower bound)
-                            if (sqrtf(__double2float_ru(da)) * 1.000001f + mv < lim) {
-                                hard = false;
-                                // still the nearest, but it may have left the radius: then there is no
-                                // correspondence (and nothing to remember: corr_s doubles as the list)
-                                if (!ctx.row_known(prior, vt, da, vs, pp.r2, x, MODE == 1 ? nt : nullptr)) corr_s[slot] = -1;
-                            }
-                        } else {
-                            // a two-candidate entry: if both are still nearer than anything else can be, the
-                            // winner between them is taken in double
-                            const int other = second_s[slot];
-                            if (other >= 0) {
-                                const double *up = G.xyz + kPtStride * (int64_t)other;
-                                const double vu[3] = {up[0], up[1], up[2]};
-                                const double db = l2_exact(vs[0], vs[1], vs[2], vu);
-                                if (sqrtf(__double2float_ru(fmax(da, db))) * 1.000001f + mv < lim) {
-                                    hard = false;
-                                    const bool first = da < db || (da == db && __ldg(G.orig + prior) < __ldg(G.orig + other));
-                                    if (!first) { corr_s[slot] = other; second_s[slot] = prior; }
-                                    const bool ok = first ? ctx.row_known(prior, vt, da, vs, pp.r2, x)
-                                                          : ctx.row_known(other, vu, db, vs, pp.r2, x);
-                                    if (!ok) corr_s[slot] = -1;
+                const HotRec h = hot[slot];
+                int match = -1;
+                if (pp.use_cache && h.c0 >= 0) {
+                    const float4 t0 = __ldg(G.hi + h.c0);
+                    const float ax = c.qx - t0.x, ay = c.qy - t0.y, az = c.qz - t0.z;
+                    const float d0 = fmaf(az, az, fmaf(ay, ay, ax * ax));
+                    // |q - c0| (upper bound) + move since the proof (upper bound) < distance to anything else then
+                    // (lower bound); a NaN or zero limit (knows nothing) compares false
+                    if (reach_now(d0 + band(G.p, d0), cum_eps) < h.lim1) {
+                        match = h.c0;
+                    } else {
+                        const ColdRec kc = cold[slot];
+                        VB_STAT(19, kc.c1 >= 0);
+                        if (kc.c1 >= 0 && cum_eps < kc.limK) {
+                            VB_STAT(14, 1);
+                            // the candidate set: is the nearest of the four nearer than anything outside can be?
+                            const float4 t1 = __ldg(G.hi + kc.c1);
+                            float4 t2 = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.0f), t3 = t2;
+                            if (kc.c2 >= 0) t2 = __ldg(G.hi + kc.c2);
+                            if (kc.c3 >= 0) t3 = __ldg(G.hi + kc.c3);
+                            const float bx = c.qx - t1.x, by = c.qy - t1.y, bz = c.qz - t1.z;
+                            const float cx = c.qx - t2.x, cy = c.qy - t2.y, cz = c.qz - t2.z;
+                            const float ex = c.qx - t3.x, ey = c.qy - t3.y, ez = c.qz - t3.z;
+                            const float d1 = fmaf(bz, bz, fmaf(by, by, bx * bx));
+                            const float d2 = fmaf(cz, cz, fmaf(cy, cy, cx * cx));
+                            const float d3 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                            const float dmin = fminf(fminf(d0, d1), fminf(d2, d3));
+                            if (reach_now(dmin + band(G.p, dmin), cum_eps) < kc.limK) {
+                                VB_STAT(15, 1);
+                                // the f32-nearest member, and the nearest of the others
+                                int w = 0;
+                                float bw = d0;
+                                if (d1 < bw) { w = 1; bw = d1; }
+                                if (d2 < bw) { w = 2; bw = d2; }
+                                if (d3 < bw) { w = 3; bw = d3; }
+                                float rest = fminf(fminf(w == 0 ? 3.0e38f : d0, w == 1 ? 3.0e38f : d1),
+                                                   fminf(w == 2 ? 3.0e38f : d2, w == 3 ? 3.0e38f : d3));
+                                if (!(rest - bw > band(G.p, bw) + band(G.p, rest))) {
+                                    w = settle_set_exact(G, vs[0], vs[1], vs[2], h.c0, kc.c1, kc.c2, kc.c3);
+                                    rest = fminf(fminf(w == 0 ? 3.0e38f : d0, w == 1 ? 3.0e38f : d1),
+                                                 fminf(w == 2 ? 3.0e38f : d2, w == 3 ? 3.0e38f : d3));
+                                }
+                                match = w == 0 ? h.c0 : (w == 1 ? kc.c1 : (w == 2 ? kc.c2 : kc.c3));
+                                // A fresh single-candidate bound, valid as of NOW: the set's other members are at
+                                // least sqrt(rest - band) away, everything outside it at least limK - cum_now.
+                                const float others = fmaxf(rest - band(G.p, rest), 0.0f);
+                                const float outside = __fsub_rd(kc.limK, cum_eps);
+                                HotRec hn;
+                                hn.c0 = match;
+                                hn.lim1 = __fadd_rd(fminf(__fmul_rd(__fsqrt_rd(others), 0.999999f), outside), cum);
+                                hot[slot] = hn;
+                                if (w != 0) {
+                                    ColdRec kn = kc;
+                                    if (w == 1) kn.c1 = h.c0; else if (w == 2) kn.c2 = h.c0; else kn.c3 = h.c0;
+                                    cold[slot] = kn;
                                 }
                             }
                         }
                     }
                 }
-#elif !defined(VB_NO_NN_CACHE)
-                const int prior = pp.use_cache ? corr_s[slot] : -1;
-#ifdef VB_PA_PRETEST
-                // how far the point has moved since its last search is known from the streamed cache entry alone:
-                // unless that is less than the entry's bound neither test below can succeed, and the gather of
-                // the match is skipped (every point, in an alignment's first iterations)
-                bool may_hold = false;
-                if (prior >= 0) {
-                    const NNCache m0 = cache[slot];
-                    const float ax = c.qx - m0.qx, ay = c.qy - m0.qy, az = c.qz - m0.qz;
-                    may_hold = sqrtf(fmaf(az, az, fmaf(ay, ay, ax * ax))) * 1.000001f + pp.pos_err <
-                               sqrtf(fabsf(m0.sec)) * 0.999999f;  // NaN (no cache) compares false
+                if (match >= 0) {
+                    hard = false;
+                    // still the nearest, but it may have left the radius: then there is no correspondence
+                    // (and nothing to remember: c0 doubles as the correspondence list)
+                    if (!ctx.row_of(match, vs, pp.r2, x)) hot[slot].c0 = -1;
                 }
-                if (may_hold) {
-#else
-                if (prior >= 0) {
-#endif
-                    const NNCache m = cache[slot];
-                    const float4 t = __ldg(G.hi + prior);
-                    const float dx = c.qx - t.x, dy = c.qy - t.y, dz = c.qz - t.z;
-                    const float d1 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    const float mx = c.qx - m.qx, my = c.qy - m.qy, mz = c.qz - m.qz;
-                    const float moved = sqrtf(fmaf(mz, mz, fmaf(my, my, mx * mx)));
-                    // |q - b| (upper bound) + move (upper bound) < distance to anything else then (lower bound);
-                    // NaN (no cache) compares false
-                    const float lhs = sqrtf(d1 + band(G.p, d1)) * 1.000001f + moved * 1.000001f + pp.pos_err;
-                    if (lhs < sqrtf(m.sec) * 0.999999f) {
-                        hard = false;
-                        // still the nearest, but it may have left the radius: then there is no correspondence
-                        // (and nothing to remember: corr_s doubles as the correspondence list)
-                        if (!ctx.row_of(prior, vs, pp.r2, x)) corr_s[slot] = -1;
-                    } else if (m.sec < 0.0f) {
-                        // a two-candidate entry (winner and runner-up too close to tell apart for long): if both
-                        // are still nearer than anything else can be, the winner between them is taken in double
-                        const int other = second_s[slot];
-                        if (other >= 0) {
-                            const float4 u = __ldg(G.hi + other);
-                            const float ex = c.qx - u.x, ey = c.qy - u.y, ez = c.qz - u.z;
-                            const float dm = fmaxf(d1, fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
-                            const float lhs2 = sqrtf(dm + band(G.p, dm)) * 1.000001f + moved * 1.000001f + pp.pos_err;
-                            if (lhs2 < sqrtf(-m.sec) * 0.999999f) {
-                                hard = false;
-                                const double da = l2_exact(vs[0], vs[1], vs[2], G.xyz + kPtStride * (int64_t)prior);
-                                const double db = l2_exact(vs[0], vs[1], vs[2], G.xyz + kPtStride * (int64_t)other);
-                                const bool first = da < db || (da == db && __ldg(G.orig + prior) < __ldg(G.orig + other));
-                                if (!first) { corr_s[slot] = other; second_s[slot] = prior; }
-                                if (!ctx.row_of(first ? prior : other, vs, pp.r2, x)) corr_s[slot] = -1;
-                            }
-                        }
-                    }
-                }
-#endif
             }
         }
-#ifdef VB_STATS
-        if (valid) {
-            const int pr = corr_s[task.corr_begin + local];
-            VB_STAT(12, hard);
-            VB_STAT(13, hard && pr < 0);
-            VB_STAT(14, hard && pr >= 0 && !(cache[task.corr_begin + local].sec >= 0.0f));
-        }
-#endif
-        // (Prefetching the next batch's streams and the match's rows ahead of the arithmetic was measured
-        // slower — 0.089 vs 0.084 ms for a settled pass: at 48 warps per SM the gathers already overlap.)
+        VB_STAT(12, hard);
+        VB_STAT(13, valid && !hard);
         const unsigned hm = __ballot_sync(0xffffffffu, hard);
         if (hard) my_hard[nhard + __popc(hm & ((1u << lane) - 1u))] = (unsigned char)(k * 32 + lane);
         nhard += __popc(hm);
@@ -493,14 +492,12 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
         for (int w = 1; w < kPassWarps; w++) { t.x += red[w * 32 + lane].x; t.y += red[w * 32 + lane].y; }
         out[lane] = t;
     }
-    // nothing listed: part B's warps for this block exit on their first load, so their rows are zeroed here
+    // nothing listed: part B never visits this block, so its rows are zeroed here
     int total = 0;
 #pragma unroll
     for (int w = 0; w < kPassWarps; w++) total += listed[w];
     if (total == 0) out[(kPart / 2) + threadIdx.x] = make_double2(0.0, 0.0);  // 4 rows x 32 double2 = 128 threads
-#ifdef VB_PB_WORKLIST
     else if (threadIdx.x == 0) pp.work[atomicAdd(pp.work_ctr + 2 * pp.parity, 1)] = blockIdx.x;
-#endif
 }
 
 // entry t of the 32 estimator slots from a summed 8x8 Gram matrix D.  Slot layout: point-to-plane 0..20 JTJ
@@ -526,141 +523,24 @@ __device__ __forceinline__ double slot_from_gram(const double *D, bool plane, in
     return v;
 }
 
-__device__ void solve_from_totals(const double *tot, double npts, ProbState *st, const SolveParams &sp, int pass_index);
-
-// The iteration tail run by the last part-B warp of a problem (kept out of line: it is rare and register-hungry).
-static __device__ __noinline__ void iteration_tail(const ProbDesc pd, const double *partials, int *ctr, double *scratch,
-                                                   bool plane, ProbState *st, const SolveParams &sp, int pass_index) {
+// ---- pass, part B: the listed points, 32 searches at a time with every lane busy, over a worklist.  Part A
+// appends the blocks that listed anything (one atomic per such block); this is a resident grid whose WARPS each
+// take (block, warp) items off the list one at a time (an atomic per item: dynamic balance in an alignment's
+// first iterations, when every block is listed, and a near-empty launch once it has settled) until none is left.
+// Which warp handles an item is arbitrary; what it computes and where it writes — the item's own partial row,
+// the points' own records — is not, so the results do not depend on it.  Each search refreshes the point's records.
+template <int MODE>
+__global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass_b_wl(
+    GridDev G, const double *__restrict__ src_xyz, const BlockTask *__restrict__ tasks,
+    const ProbState *__restrict__ states, double *partials, HotRec *__restrict__ hot, ColdRec *__restrict__ cold,
+    const unsigned char *__restrict__ hard_ids, const int *__restrict__ hard_cnt, PassParams pp) {
     const int lane = threadIdx.x & 31;
-    __threadfence();
-    if (lane == 0) *ctr = 0;  // ready for the next pass
-    const double2 *rows = reinterpret_cast<const double2 *>(partials + (int64_t)pd.blk_begin * kRowsPerBlock * kPart) + lane;
-    const int nrows = pd.blk_count * kRowsPerBlock;
-    double ax = 0.0, ay = 0.0;  // entries 2*lane, 2*lane + 1 of the summed Gram matrix; rows added in index order
-    int r = 0;
-    for (; r + 8 <= nrows; r += 8) {
-        double2 v[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = __ldcg(rows + (int64_t)(r + i) * (kPart / 2));  // written by other SMs
-#pragma unroll
-        for (int i = 0; i < 8; i++) { ax += v[i].x; ay += v[i].y; }
-    }
-    for (; r < nrows; r++) {
-        const double2 v = __ldcg(rows + (int64_t)r * (kPart / 2));
-        ax += v.x; ay += v.y;
-    }
-    __syncwarp();
-    double *D = scratch, *tot = scratch + kPart;
-    D[2 * lane] = ax; D[2 * lane + 1] = ay;
-    __syncwarp();
-    tot[lane] = slot_from_gram(D, plane, lane);
-    __syncwarp();
-    if (lane == 0) solve_from_totals(tot, (double)pd.npts, st, sp, pass_index);
-}
-
-// ---- pass, part B: the listed points of a part-A block, 32 searches at a time with every lane busy.  Each
-// search refreshes the point's cache entry.  One WARP per CUDA block (grid = 4 x part A's): once an alignment
-// settles most lists hold a handful of points, and single-warp blocks let an SM keep ~24 of those short,
-// latency-bound batches in flight instead of 6 four-warp blocks with one live warp each.
-template <int MODE>
-__global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b(
-    GridDev G, const double *__restrict__ src_xyz, const BlockTask *__restrict__ tasks,
-    ProbState *states, double *partials, int *__restrict__ corr_s,
-    NNCache *__restrict__ cache, int *__restrict__ second_s, const unsigned char *__restrict__ hard_ids,
-    const int *__restrict__ hard_cnt, PassParams pp, const ProbDesc *__restrict__ probs, int *prob_ctr, SolveParams sp, int pass_index, int fuse_solve) {
-    const int blk = blockIdx.x / kPassWarps, warp = blockIdx.x % kPassWarps, lane = threadIdx.x;
-    // the block's list = its warps' lists of part A, concatenated
-    int seg_end[kPassWarps];
-    int total = 0;
-#pragma unroll
-    for (int w = 0; w < kPassWarps; w++) {
-        total += hard_cnt[blk * kPassWarps + w];
-        seg_end[w] = total;
-    }
-    // Nothing to search (most blocks once an alignment settles): part A has zeroed this warp's partial row.
-    // (hard_cnt of a finished problem is stale; its rows are never read again, so either exit is fine.)
-    if (total == 0 && !fuse_solve) return;
-    const BlockTask task = tasks[blk];
-    const ProbState *st = states + task.prob;
-    if (st->done) return;
-    __shared__ WarpScratch ws;
-    PassCtx<MODE> ctx(G, st->T);
-#pragma unroll 1
-    for (int h0 = 32 * warp; h0 < total; h0 += 32 * kPassWarps) {
-        const bool live = h0 + lane < total;
-        double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        double vs[3] = {0, 0, 0}, d2 = 0.0;
-        QueryCtx c;
-        int prior = -1, slot = 0;
-        float slack = 0.0f;
-        if (live) {
-            const int h = h0 + lane;
-            int w = 0, base = 0;
-#pragma unroll
-            for (int i = 0; i < kPassWarps - 1; i++)
-                if (h >= seg_end[i]) { w = i + 1; base = seg_end[i]; }
-            const int id = hard_ids[((int64_t)blk * kPassWarps + w) * (32 * kPtsPerThread) + (h - base)];
-            const int local = (w * kPtsPerThread + (id >> 5)) * 32 + (id & 31);
-            slot = task.corr_begin + local;
-            ctx.transform(src_xyz + 3 * (int64_t)(task.src_begin + local), vs);
-            make_query(G.p, vs[0], vs[1], vs[2], c);  // inside the grid, or it would not be listed
-            prior = corr_s[slot];  // last iteration's match: a bound for this search
-            // looking further than the answer needs only pays when the point is about to settle: one that
-            // has just moved by more than the slack will fail the next test anyway
-            const NNCache m = cache[slot];
-            const float mx = c.qx - m.qx, my = c.qy - m.qy, mz = c.qz - m.qz;
-            if (fmaf(mz, mz, fmaf(my, my, mx * mx)) < 4.0f * pp.slack * pp.slack) slack = pp.slack;  // NaN: no
-        }
-        float sec = -1.0f;
-        int other = -1;
-#ifdef VB_SEARCH_COOP_ONLY
-        const int bs = nn_search_warp(G, live, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, &d2);
-#else
-        const int bs = nn_search_hybrid<32>(G, live, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, prior, ws.runs, &d2,
-                                            slack, &sec, VB_COOP_WARP_LANES, &other);
-#endif
-        if (live) {
-            corr_s[slot] = bs;  // sorted position; vb200_batch_corr maps it to the caller's index
-            NNCache m;
-            m.qx = c.qx; m.qy = c.qy; m.qz = c.qz;
-            m.sec = bs >= 0 ? sec : -1.0f;
-            cache[slot] = m;
-            second_s[slot] = bs >= 0 ? other : -1;
-            if (bs >= 0) ctx.row_of(bs, vs, pp.r2, x);
-        }
-        ctx.accumulate(ws.rows, x);
-    }
-    ctx.write_partial(partials + ((int64_t)blk * kRowsPerBlock + 1 + warp) * kPart);
-    if (!fuse_solve) return;
-    // ---- iteration tail, fused: the LAST warp of a problem to get here (all of the problem's partial rows are
-    // then in memory) sums them in a fixed order and takes the estimator step — no separate solve launch.
-    __threadfence();
-    int prev = 0;
-    if (lane == 0) prev = atomicAdd(prob_ctr + task.prob, 1);
-    prev = __shfl_sync(0xffffffffu, prev, 0);
-    const ProbDesc pd = probs[task.prob];
-    if (prev != pd.blk_count * kPassWarps - 1) return;
-    iteration_tail(pd, partials, prob_ctr + task.prob, ws.rows, MODE == 1, states + task.prob, sp, pass_index);
-}
-
-#ifdef VB_PB_WORKLIST
-// ---- pass, part B over a worklist.  k_pass_b above launches one single-warp block per (part-A block, warp):
-// 12 544 blocks on the BASELINE workload, nearly all of which find an empty list once an alignment settles, and
-// in the first iterations the block scheduler's fixed order leaves a tail.  Here part A appends the blocks that listed anything to a worklist (one atomic per such block) and part B is a
-// resident grid of single-warp blocks, each of which takes (block, warp) items off the list one at a time (an
-// atomic per item: dynamic balance in the first iterations, when every block is listed) until none is left.
-// Which warp handles an item is arbitrary; what it computes and where it writes (the item's own partial row,
-// the points' own slots) is not: results are bit for bit those of k_pass_b.
-template <int MODE>
-__global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b_wl(
-    GridDev G, const double *__restrict__ src_xyz, const BlockTask *__restrict__ tasks,
-    const ProbState *__restrict__ states, double *partials, int *__restrict__ corr_s,
-    NNCache *__restrict__ cache, int *__restrict__ second_s, const unsigned char *__restrict__ hard_ids,
-    const int *__restrict__ hard_cnt, PassParams pp) {
-    const int lane = threadIdx.x;
-    __shared__ WarpScratch ws;
+    __shared__ WarpScratch wss[kPassWarps];
+    WarpScratch &ws = wss[threadIdx.x >> 5];
+    pdl_launch_dependents();
+    pdl_wait();  // part A has finished: the worklist and its length are final
     int *ctr = pp.work_ctr + 2 * pp.parity;
-    const int n_items = ctr[0] * kPassWarps;  // final: part A has finished
+    const int n_items = ctr[0] * kPassWarps;
 #pragma unroll 1
     for (;;) {
         int item = 0;
@@ -676,7 +556,15 @@ __global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b_wl(
             seg_end[w] = total;
         }
         const BlockTask task = tasks[blk];
-        PassCtx<MODE> ctx(G, states[task.prob].T);  // (a finished problem's blocks are never listed)
+        const ProbState *st = states + task.prob;  // (a finished problem's blocks are never listed)
+        PassCtx<MODE> ctx(G, st->T);
+        const float cum = st->cum;
+        // A problem whose latest update moved it by little is settling: its searches look further than the answer
+        // needs (as far as everything the problem is still expected to move) and keep candidate sets, so that the
+        // next small moves are settled by part A.  One that has just jumped will fail any such test anyway.
+        const float last_move = st->last_move;
+        const bool settling = last_move < pp.set_move;
+        const float slack = settling ? fminf(fmaxf(last_move * (VB_SLACK_MOVE_PCT * 0.01f), pp.slack_lo), pp.slack_hi) : 0.0f;
 #pragma unroll 1
         for (int h0 = 32 * warp; h0 < total; h0 += 32 * kPassWarps) {
             const bool live = h0 + lane < total;
@@ -684,7 +572,6 @@ __global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b_wl(
             double vs[3] = {0, 0, 0}, d2 = 0.0;
             QueryCtx c;
             int prior = -1, slot = 0;
-            float slack = 0.0f;
             if (live) {
                 const int h = h0 + lane;
                 int w = 0, base = 0;
@@ -695,23 +582,21 @@ __global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b_wl(
                 const int local = (w * kPtsPerThread + (id >> 5)) * 32 + (id & 31);
                 slot = task.corr_begin + local;
                 ctx.transform(src_xyz + 3 * (int64_t)(task.src_begin + local), vs);
-                make_query(G.p, vs[0], vs[1], vs[2], c);
-                prior = corr_s[slot];
-                const NNCache m = cache[slot];
-                const float mx = c.qx - m.qx, my = c.qy - m.qy, mz = c.qz - m.qz;
-                if (fmaf(mz, mz, fmaf(my, my, mx * mx)) < 4.0f * pp.slack * pp.slack) slack = pp.slack;
+                make_query(G.p, vs[0], vs[1], vs[2], c);  // inside the grid, or it would not be listed
+                prior = hot[slot].c0;  // last iteration's match: a bound for this search
             }
-            float sec = -1.0f;
-            int other = -1;
+            SearchProof proof;
             const int bs = nn_search_hybrid<32>(G, live, c, vs[0], vs[1], vs[2], pp.r2, pp.r2_ub, prior, ws.runs, &d2,
-                                                slack, &sec, VB_COOP_WARP_LANES, &other);
+                                                slack, &proof, VB_COOP_WARP_LANES, settling);
             if (live) {
-                corr_s[slot] = bs;
-                NNCache m;
-                m.qx = c.qx; m.qy = c.qy; m.qz = c.qz;
-                m.sec = bs >= 0 ? sec : -1.0f;
-                cache[slot] = m;
-                second_s[slot] = bs >= 0 ? other : -1;
+                HotRec hn;
+                hn.c0 = bs;  // sorted position; vb200_batch_corr maps it to the caller's index
+                hn.lim1 = bs >= 0 ? lim_of(proof.sec1, cum) : 0.0f;
+                hot[slot] = hn;
+                ColdRec kn;
+                kn.c1 = proof.others[0]; kn.c2 = proof.others[1]; kn.c3 = proof.others[2];
+                kn.limK = bs >= 0 ? lim_of(proof.secK, cum) : 0.0f;
+                cold[slot] = kn;
                 if (bs >= 0) ctx.row_of(bs, vs, pp.r2, x);
             }
             ctx.accumulate(ws.rows, x);
@@ -720,7 +605,6 @@ __global__ void __launch_bounds__(32, 4 * VB_PASS_MINBLOCKS) k_pass_b_wl(
         __syncwarp();
     }
 }
-#endif
 
 // ---- estimator solves from the reduced slots ---------------------------------------------------------
 __device__ void update_p2plane(const double *tot, const SolveParams &sp, double *U) {
@@ -773,79 +657,34 @@ __device__ void update_p2p(const double *tot, const double *cref, double *U) {
     }
 }
 
-// Fixed-order reduction of one problem's per-warp partials (8x8 Gram matrices, kPart doubles each) into the
-// 32 estimator slots tot[kAcc] (shared memory); 256 threads.  Slot layout: point-to-plane 0..20 JTJ upper
-// triangle row-major, 21..26 JTr; point-to-point 0..2 sum s', 3..5 sum d', 6..14 sum d' s'^T, 15 sum |s'|^2;
-// both 30 = sum d2, 31 = count.
-__device__ __forceinline__ void reduce_partials(const ProbDesc &pd, const double *__restrict__ partials,
-                                                const int *__restrict__ hard_cnt, bool plane,
-                                                double (*sw)[kPart], double *tot) {
-    const int e = threadIdx.x & (kPart - 1), grp = threadIdx.x / kPart;  // 4 groups of 64 threads
-    double s = 0.0;
-    const double *col = partials + (int64_t)pd.blk_begin * kRowsPerBlock * kPart + e;
-#ifdef VB_SOLVE_SKIP
-    // Part-B rows of blocks whose list was empty are zeros (k_pass_a wrote them): not loading them leaves every
-    // sum's bits alone (s + 0.0 == s; s is never -0.0) and, once an alignment settles, four fifths of the rows
-    // are such zeros.  Which blocks listed anything is read ONCE per chunk of blocks into shared memory — one
-    // coalesced 16-byte load per block — so no row has a dependent global load in front of it (the first attempt
-    // looked the count up per row and was slower than loading the zeros).  Rows keep their group and their
-    // position in the chain of adds: a chunk is a whole number of 64-row steps.
-    constexpr int kFlagChunk = 2048;  // blocks per chunk
-    static_assert(kPassWarps == 4 && (kFlagChunk * kRowsPerBlock) % (4 * 16) == 0, "chunk = whole unrolled steps");
-    __shared__ unsigned char listed[kFlagChunk];
-    for (int c0 = 0; c0 < pd.blk_count; c0 += kFlagChunk) {
-        const int nb = min(kFlagChunk, pd.blk_count - c0);
-        __syncthreads();  // the previous chunk's flags have been consumed
-        for (int j = threadIdx.x; j < nb; j += blockDim.x) {
-            const int4 h = reinterpret_cast<const int4 *>(hard_cnt)[pd.blk_begin + c0 + j];
-            listed[j] = (h.x | h.y | h.z | h.w) != 0;
+// Upper bound of |U q - q| over the points q of a problem whose cloud has bounding sphere (ctr, rad) in its own
+// frame and current transform T: |(R_u - I)(q - c) + (R_u - I) c + t_u| <= ||R_u - I||_F * smax(R_T) * rad + |...c...|
+// with c = T ctr.  smax(R_T) <= sqrt(max row sum of |R_T^T R_T|) (1 for a rotation; init may be anything).
+__device__ double update_move_bound(const double *U, const double *T, const double *ctr, double rad) {
+    const double c[3] = {T[0] * ctr[0] + T[1] * ctr[1] + T[2] * ctr[2] + T[3],
+                         T[4] * ctr[0] + T[5] * ctr[1] + T[6] * ctr[2] + T[7],
+                         T[8] * ctr[0] + T[9] * ctr[1] + T[10] * ctr[2] + T[11]};
+    double fro = 0.0, dc2 = 0.0, s2 = 0.0;
+    for (int r = 0; r < 3; r++) {
+        double dc = U[4 * r + 3];
+        for (int k = 0; k < 3; k++) {
+            const double m = U[4 * r + k] - (r == k ? 1.0 : 0.0);
+            fro += m * m;
+            dc += m * c[k];
         }
-        __syncthreads();
-        const int r0 = c0 * kRowsPerBlock, r1 = r0 + nb * kRowsPerBlock;
-        for (int b = r0 + grp; b < r1; b += 4 * 16) {
-            double v[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int r = b + 4 * i;
-                const int blk = r / kRowsPerBlock;
-                const bool need = r < r1 && (r == blk * kRowsPerBlock || listed[min(blk - c0, kFlagChunk - 1)]);
-                v[i] = need ? col[(int64_t)r * kPart] : 0.0;
-            }
-#pragma unroll
-            for (int i = 0; i < 16; i++) s += v[i];
-        }
+        dc2 += dc * dc;
+        double row = 0.0;  // row r of |R^T R|
+        for (int k = 0; k < 3; k++) row += fabs(T[r] * T[k] + T[4 + r] * T[4 + k] + T[8 + r] * T[8 + k]);
+        s2 = fmax(s2, row);
     }
-#else
-    // rows in index order per group.  (Skipping the part-B rows of blocks with an empty list was measured
-    // slower: the count lookup puts a dependent load in front of every row.)
-    (void)hard_cnt;
-    // kSolveInflight independent loads in flight per thread (the rows sit in L2; the chain of adds keeps its fixed
-    // order whatever the batch size, so this knob never changes a bit of the result)
-#ifndef VB_SOLVE_INFLIGHT
-#define VB_SOLVE_INFLIGHT 16
-#endif
-    constexpr int kSolveInflight = VB_SOLVE_INFLIGHT;
-    const int nrows = pd.blk_count * kRowsPerBlock;
-    // (the ragged last batch is predicated, not a loop of dependent loads: adding +0.0 leaves the sum's bits alone)
-    for (int b = grp; b < nrows; b += 4 * kSolveInflight) {
-        double v[kSolveInflight];
-#pragma unroll
-        for (int i = 0; i < kSolveInflight; i++) v[i] = b + 4 * i < nrows ? col[(int64_t)(b + 4 * i) * kPart] : 0.0;
-#pragma unroll
-        for (int i = 0; i < kSolveInflight; i++) s += v[i];
-    }
-#endif
-    sw[grp][e] = s;
-    __syncthreads();
-    if (threadIdx.x < kPart) sw[0][e] = ((sw[0][e] + sw[1][e]) + sw[2][e]) + sw[3][e];
-    __syncthreads();
-    if (threadIdx.x < kAcc) tot[threadIdx.x] = slot_from_gram(sw[0], plane, threadIdx.x);
-    __syncthreads();
+    const double d = (sqrt(dc2) + sqrt(fro) * sqrt(s2) * rad) * (1.0 + 1e-9) + 1e-12;
+    return d == d ? d : 1e30;  // a NaN update (never produced by the estimators) invalidates every cached bound
 }
 
 // result bookkeeping (Registration.cpp:87-93), convergence test (:179-183) and estimator update (:172-174)
 // from the reduced slots; one thread.  npts = source points the totals were accumulated over.
-__device__ void solve_from_totals(const double *tot, double npts, ProbState *st, const SolveParams &sp, int pass_index) {
+__device__ void solve_from_totals(const double *tot, double npts, const ProbDesc &pd, ProbState *st,
+                                  const SolveParams &sp, int pass_index) {
     const double K = tot[kSlotCount];
     double fitness = 0.0, rmse = 0.0;
     if (K > 0.0 && npts > 0.0) {
@@ -876,22 +715,93 @@ __device__ void solve_from_totals(const double *tot, double npts, ProbState *st,
     } else {
         update_p2plane(tot, sp, U);
     }
+    const float moved = __double2float_ru(update_move_bound(U, T, pd.ctr, pd.rad));
+    st->last_move = moved;
+    st->cum = __fadd_ru(st->cum, moved);
     mat4_mul(U, T, T);
     for (int i = 0; i < 16; i++) st->T[i] = T[i];
     st->iters = pass_index + 1;
 }
 
-// One block per problem: reduce + solve (the single-GPU iteration tail).
+// Fixed-order reduction of rows [r0, r1) of the partial Gram matrices (kPart doubles each) into sw[0][0..63];
+// 256 threads = 4 groups of 64, group g takes rows r0 + g, r0 + g + 4, ... in index order, the groups are then
+// added in group order.  kSolveInflight independent loads in flight per thread; the chain of adds keeps its fixed
+// order whatever the batch size.
+constexpr int kSolveInflight = 16;
+__device__ __forceinline__ void reduce_rows(const double *__restrict__ rows, int r0, int r1, double (*sw)[kPart]) {
+    const int e = threadIdx.x & (kPart - 1), grp = threadIdx.x / kPart;
+    double s = 0.0;
+    const double *col = rows + e;
+    // (the ragged last batch is predicated, not a loop of dependent loads: adding +0.0 leaves the sum's bits alone)
+    for (int b = r0 + grp; b < r1; b += 4 * kSolveInflight) {
+        double v[kSolveInflight];
+#pragma unroll
+        for (int i = 0; i < kSolveInflight; i++) v[i] = b + 4 * i < r1 ? __ldcg(col + (int64_t)(b + 4 * i) * kPart) : 0.0;
+#pragma unroll
+        for (int i = 0; i < kSolveInflight; i++) s += v[i];
+    }
+    sw[grp][e] = s;
+    __syncthreads();
+    if (threadIdx.x < kPart) sw[0][e] = ((sw[0][e] + sw[1][e]) + sw[2][e]) + sw[3][e];
+    __syncthreads();
+}
+
+// One CLUSTER of kSolveCtas blocks per problem: each block sums a contiguous eighth of the problem's partial rows
+// (one round trip to L2 with every load in flight instead of a 32-block kernel walking ~500 rows each), block 0
+// adds the eight sums in rank order through distributed shared memory and takes the estimator step.  The order
+// of every addition is fixed by the problem's own row count: same bits run to run, alone or in a batch.
+constexpr int kSolveCtas = 8;
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem_f64(const double *local_smem_ptr, unsigned rank) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(local_smem_ptr), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+// the cluster's reduction: afterwards block 0's tot[0..31] holds the problem's estimator slots
+__device__ __forceinline__ void cluster_reduce_partials(const ProbDesc &pd, const double *__restrict__ partials,
+                                                        bool plane, double (*sw)[kPart], double *tot) {
+    const unsigned rank = cluster_ctarank();
+    const int nrows = pd.blk_count * kRowsPerBlock;
+    const int per = (nrows + kSolveCtas - 1) / kSolveCtas;
+    const int r0 = min((int)rank * per, nrows), r1 = min(r0 + per, nrows);
+    reduce_rows(partials + (int64_t)pd.blk_begin * kRowsPerBlock * kPart, r0, r1, sw);
+    cluster_sync_all();  // every block's sw[0] is final and visible cluster-wide
+    if (rank == 0) {
+        if (threadIdx.x < kPart) {
+            double t = sw[0][threadIdx.x];
+#pragma unroll
+            for (unsigned r = 1; r < kSolveCtas; r++) t += ld_dsmem_f64(&sw[0][threadIdx.x], r);
+            sw[1][threadIdx.x] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < kAcc) tot[threadIdx.x] = slot_from_gram(sw[1], plane, threadIdx.x);
+        __syncthreads();
+    }
+    cluster_sync_all();  // nobody exits while block 0 may still read its shared memory
+}
+
 __global__ void __launch_bounds__(256) k_solve(const ProbDesc *__restrict__ probs, ProbState *__restrict__ states,
-                                               const double *__restrict__ partials,
-                                               const int *__restrict__ hard_cnt, SolveParams sp, int pass_index) {
-    const ProbDesc pd = probs[blockIdx.x];
-    ProbState *st = states + blockIdx.x;
-    if (st->done) return;
+                                               const double *__restrict__ partials, SolveParams sp, int pass_index) {
+    const int p = blockIdx.x / kSolveCtas;
+    const ProbDesc pd = probs[p];  // static since set_problems
+    pdl_launch_dependents();
+    pdl_wait();  // both parts of the pass have written their partial rows
+    ProbState *st = states + p;
+    if (st->done) return;  // (cluster-uniform)
     __shared__ double sw[4][kPart];
     __shared__ double tot[kAcc];
-    reduce_partials(pd, partials, hard_cnt, sp.estimator != VB200_EST_P2P, sw, tot);
-    if (threadIdx.x == 0) solve_from_totals(tot, (double)pd.npts, st, sp, pass_index);
+    cluster_reduce_partials(pd, partials, sp.estimator != VB200_EST_P2P, sw, tot);
+    if (cluster_ctarank() == 0 && threadIdx.x == 0) solve_from_totals(tot, (double)pd.npts, pd, st, sp, pass_index);
 }
 
 // The same tail split in two for multi-GPU alignment of ONE cloud sharded over ranks (ICPRefinement's global
@@ -899,20 +809,21 @@ __global__ void __launch_bounds__(256) k_solve(const ProbDesc *__restrict__ prob
 // caller all-reduces across GPUs, k_solve_totals finishes the iteration from the combined totals.  Every rank
 // sees identical totals, hence applies the identical update: no broadcast of T is needed.
 __global__ void __launch_bounds__(256) k_reduce(const ProbDesc *__restrict__ probs, const ProbState *__restrict__ states,
-                                                const double *__restrict__ partials,
-                                                const int *__restrict__ hard_cnt, bool plane,
+                                                const double *__restrict__ partials, bool plane,
                                                 double *__restrict__ totals) {
-    const ProbDesc pd = probs[blockIdx.x];
+    const int p = blockIdx.x / kSolveCtas;
+    const ProbDesc pd = probs[p];
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ double sw[4][kPart];
     __shared__ double tot[kAcc];
-    if (states[blockIdx.x].done) {  // finished problems contribute their last totals unchanged
-        return;
-    }
-    reduce_partials(pd, partials, hard_cnt, plane, sw, tot);
-    if (threadIdx.x < kAcc) totals[(int64_t)blockIdx.x * kAcc + threadIdx.x] = tot[threadIdx.x];
+    if (states[p].done) return;  // finished problems contribute their last totals unchanged
+    cluster_reduce_partials(pd, partials, plane, sw, tot);
+    if (cluster_ctarank() == 0 && threadIdx.x < kAcc) totals[(int64_t)p * kAcc + threadIdx.x] = tot[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(32) k_solve_totals(int P, ProbState *__restrict__ states,
+__global__ void __launch_bounds__(32) k_solve_totals(int P, const ProbDesc *__restrict__ probs,
+                                                     ProbState *__restrict__ states,
                                                      const double *__restrict__ totals,
                                                      const double *__restrict__ npts_global, SolveParams sp,
                                                      int pass_index) {
@@ -920,7 +831,7 @@ __global__ void __launch_bounds__(32) k_solve_totals(int P, ProbState *__restric
     if (p >= P || states[p].done) return;
     double tot[kAcc];
     for (int i = 0; i < kAcc; i++) tot[i] = totals[(int64_t)p * kAcc + i];
-    solve_from_totals(tot, npts_global[p], states + p, sp, pass_index);
+    solve_from_totals(tot, npts_global[p], probs[p], states + p, sp, pass_index);
 }
 
 // ---- source-cloud bucket sort (spatial coherence for the search; deterministic order) ----------------
@@ -1008,23 +919,105 @@ __global__ void __launch_bounds__(256) k_src_gather(const double *__restrict__ i
 
 // correspondences are kept as sorted scene positions (they double as the next pass's search bound); this maps
 // one problem's column to the caller's target indices
-__global__ void __launch_bounds__(256) k_corr_orig(const int *__restrict__ corr_s, int n, const int *__restrict__ orig,
+__global__ void __launch_bounds__(256) k_corr_orig(const HotRec *__restrict__ hot, int n, const int *__restrict__ orig,
                                                    int *__restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int s = corr_s[i];
+    const int s = hot[i].c0;
     out[i] = s >= 0 ? orig[s] : -1;
 }
 
-// ---- estimator plug-in kernel: reductions over an explicit correspondence list ------------------------
+// ---- per-cloud bounding sphere (what update_move_bound needs), computed once at upload ------------------
+__device__ __forceinline__ unsigned long long ordered_bits(double v) {  // monotone map double -> uint64
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ inline double from_ordered_bits(unsigned long long o) {
+    const unsigned long long u = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
+    double v;
+    memcpy(&v, &u, sizeof(v));
+    return v;
+}
+
+// bounds[c] = {min x, y, z, max x, y, z} as ordered bits (initialised to ~0 / 0 by the caller).  A warp whose
+// lanes all belong to one cloud (nearly every warp) reduces with shuffles and issues six atomics.
+__global__ void __launch_bounds__(256) k_cloud_bbox(const double *__restrict__ xyz, int n,
+                                                    const int *__restrict__ cloud_off, int ncloud,
+                                                    unsigned long long *__restrict__ bounds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const int c = valid ? find_cloud(cloud_off, ncloud, i) : -1;
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (!act) return;
+    const int c_first = __shfl_sync(0xffffffffu, c, __ffs(act) - 1);
+    const bool uniform = __all_sync(0xffffffffu, !valid || c == c_first);
+    for (int a = 0; a < 3; a++) {
+        unsigned long long lo = valid ? ordered_bits(xyz[3 * (int64_t)i + a]) : ~0ull, hi = valid ? lo : 0ull;
+        if (uniform) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+                lo = l2 < lo ? l2 : lo;
+                hi = h2 > hi ? h2 : hi;
+            }
+            if ((threadIdx.x & 31) == 0) {
+                atomicMin(bounds + 6 * c_first + a, lo);
+                atomicMax(bounds + 6 * c_first + 3 + a, hi);
+            }
+        } else if (valid) {
+            atomicMin(bounds + 6 * c + a, lo);
+            atomicMax(bounds + 6 * c + 3 + a, hi);
+        }
+    }
+}
+
+// rad2[c] = max |p - centre|^2 (bits of a non-negative double order like integers)
+__global__ void __launch_bounds__(256) k_cloud_radius(const double *__restrict__ xyz, int n,
+                                                      const int *__restrict__ cloud_off, int ncloud,
+                                                      const unsigned long long *__restrict__ bounds,
+                                                      unsigned long long *__restrict__ rad2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const int c = valid ? find_cloud(cloud_off, ncloud, i) : -1;
+    double d2 = 0.0;
+    if (valid) {
+        for (int a = 0; a < 3; a++) {
+            const double ctr = 0.5 * (from_ordered_bits(bounds[6 * c + a]) + from_ordered_bits(bounds[6 * c + 3 + a]));
+            const double d = xyz[3 * (int64_t)i + a] - ctr;
+            d2 += d * d;
+        }
+        if (!(d2 == d2)) d2 = 0.0;
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (!act) return;
+    const int c_first = __shfl_sync(0xffffffffu, c, __ffs(act) - 1);
+    unsigned long long m = (unsigned long long)__double_as_longlong(d2);
+    if (__all_sync(0xffffffffu, !valid || c == c_first)) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long m2 = __shfl_xor_sync(0xffffffffu, m, o);
+            m = m2 > m ? m2 : m;
+        }
+        if ((threadIdx.x & 31) == 0) atomicMax(rad2 + c_first, m);
+    } else if (valid) {
+        atomicMax(rad2 + c, m);
+    }
+}
+
+// ---- estimator plug-in kernels: reductions over an explicit correspondence list ------------------------
+// corr == nullptr: row i of vs_in / vt_in / nt_in is correspondence i (the host entry gathers them, as the
+// reference does, TransformationEstimation.cpp:52-57); otherwise corr[2i], corr[2i+1] index the clouds in place
+// (device-resident entry: nothing is gathered on the host).
 template <int MODE>
 __global__ void __launch_bounds__(kPassTpb) k_estimate(const double *__restrict__ vs_in,
                                                        const double *__restrict__ vt_in,
-                                                       const double *__restrict__ nt_in, int64_t K,
+                                                       const double *__restrict__ nt_in,
+                                                       const int *__restrict__ corr, int64_t K,
                                                        double *__restrict__ partials) {
     __shared__ double swarp[kPassTpb / 32][kAcc];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double cref[3] = {vs_in[0], vs_in[1], vs_in[2]};
+    const int64_t first = corr ? corr[0] : 0;
+    const double cref[3] = {vs_in[3 * first], vs_in[3 * first + 1], vs_in[3 * first + 2]};
     double acc = 0.0;
 #pragma unroll 1
     for (int k = 0; k < kPtsPerThread; k++) {
@@ -1032,14 +1025,15 @@ __global__ void __launch_bounds__(kPassTpb) k_estimate(const double *__restrict_
         bool valid = i < K;
         double vs[3] = {0, 0, 0}, vt[3] = {0, 0, 0}, nt[3] = {0, 0, 0};
         if (valid) {
+            const int64_t is = corr ? corr[2 * i] : i, it = corr ? corr[2 * i + 1] : i;
             for (int a = 0; a < 3; a++) {
-                vs[a] = vs_in[3 * i + a];
-                vt[a] = vt_in[3 * i + a];
-                if (MODE == 1) nt[a] = nt_in[3 * i + a];
+                vs[a] = vs_in[3 * is + a];
+                vt[a] = vt_in[3 * it + a];
+                if (MODE == 1) nt[a] = nt_in[3 * it + a];
             }
         }
         double v[kAcc];
-        contributions<MODE>(valid, 0.0, vs, vt, nt, cref, v);
+        contributions<MODE>(valid, vs, vt, nt, cref, v);
         acc += warp_reduce_slots(v);
     }
     swarp[warp][lane] = acc;
@@ -1051,9 +1045,12 @@ __global__ void __launch_bounds__(kPassTpb) k_estimate(const double *__restrict_
     }
 }
 
+// out[0..15] = the estimator's transformation; out[16] = sqrt(sum |s - t|^2 / K), the point-to-point
+// ComputeRMSE (src/constrained_ICP.cpp:13-23, TransformationEstimation.cpp:35-45)
 __global__ void __launch_bounds__(256) k_estimate_solve(const double *__restrict__ partials, int nblk,
-                                                        const double *__restrict__ vs_in, SolveParams sp,
-                                                        double *__restrict__ out_T) {
+                                                        const double *__restrict__ vs_in,
+                                                        const int *__restrict__ corr, SolveParams sp,
+                                                        double *__restrict__ out) {
     __shared__ double sw[8][kAcc];
     __shared__ double tot[kAcc];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1070,12 +1067,14 @@ __global__ void __launch_bounds__(256) k_estimate_solve(const double *__restrict
     if (threadIdx.x != 0) return;
     double U[16];
     if (sp.estimator == VB200_EST_P2P) {
-        const double cref[3] = {vs_in[0], vs_in[1], vs_in[2]};
+        const int64_t first = corr ? corr[0] : 0;
+        const double cref[3] = {vs_in[3 * first], vs_in[3 * first + 1], vs_in[3 * first + 2]};
         update_p2p(tot, cref, U);
     } else {
         update_p2plane(tot, sp, U);
     }
-    for (int i = 0; i < 16; i++) out_T[i] = U[i];
+    for (int i = 0; i < 16; i++) out[i] = U[i];
+    out[16] = tot[kSlotCount] > 0.0 ? sqrt(tot[kSlotRes2] / tot[kSlotCount]) : 0.0;
 }
 
 }  // namespace
@@ -1087,13 +1086,15 @@ struct Batch {
     int ncloud = 0;
     int64_t npts = 0;
     std::vector<int> cloud_off;     // host copy, ncloud+1
+    std::vector<double> cloud_sphere;  // per cloud: centre of its bounding box (3) and bounding radius about it
     bool has_normals = false;
+    bool use_cache = true;          // vb200_batch_set_option(VB200_OPT_NN_CACHE)
+    bool split_timing = false;      // vb200_batch_set_option(VB200_OPT_SPLIT_TIMING)
     double *d_src = nullptr;        // sorted source points, 3*npts
     int *d_src_orig = nullptr;      // sorted position -> original index local to its cloud
     int *d_cloud_off = nullptr;
     // problems
     int P = 0;
-    bool all_nonempty = false;               // every problem has source points (the fused iteration tail needs one)
     std::vector<ProbDesc> probs;
     int nblk = 0;
     int64_t ncorr_slots = 0;
@@ -1101,18 +1102,14 @@ struct Batch {
     ProbState *d_states = nullptr;
     BlockTask *d_tasks = nullptr;
     double *d_partials = nullptr;
-    int *d_corr = nullptr;
-    NNCache *d_cache = nullptr;              // per (problem, point): what its last search proved (k_pass_a/b)
-    int *d_second = nullptr;                 // ... and the runner-up kept with a two-candidate entry
+    HotRec *d_hot = nullptr;                 // per (problem, point): match + single-candidate bound (k_pass_a/b)
+    ColdRec *d_cold = nullptr;               // ... and the rest of its candidate set
     unsigned char *d_hard_ids = nullptr;     // per block and warp: the points part A left for part B
     int *d_hard_cnt = nullptr;
-    int *d_prob_ctr = nullptr;               // per problem: part-B warps finished in the current pass
     int *d_ndone = nullptr;                  // problems finished since set_problems
-#ifdef VB_PB_WORKLIST
     int *d_work = nullptr;                   // part-A blocks with a non-empty list (k_pass_b_wl)
     int *d_work_ctr = nullptr;               // 2 x {listed, handed out}
     int pass_parity = 0;
-#endif
     int64_t launches = 0;
     int iter_base = 0;                       // running pass index for vb200_batch_iterate
     double *d_totals = nullptr;              // P x kAcc, library-owned unless the caller supplied a buffer
@@ -1124,23 +1121,14 @@ struct Batch {
 
 static void batch_free_problems(Batch *b) {
     cudaStream_t st = b->stream;
-    void *ptrs[10] = {b->d_probs, b->d_states, b->d_tasks, b->d_partials, b->d_corr, b->d_totals, b->d_npts_global,
-                      b->d_cache, b->d_hard_ids, b->d_hard_cnt};
-    if (b->d_prob_ctr) cudaFreeAsync(b->d_prob_ctr, st);
-    if (b->d_second) cudaFreeAsync(b->d_second, st);
-    b->d_second = nullptr;
-    if (b->d_ndone) cudaFreeAsync(b->d_ndone, st);
-    b->d_ndone = nullptr;
-#ifdef VB_PB_WORKLIST
-    if (b->d_work) cudaFreeAsync(b->d_work, st);
-    if (b->d_work_ctr) cudaFreeAsync(b->d_work_ctr, st);
-    b->d_work = nullptr; b->d_work_ctr = nullptr;
-#endif
-    b->d_totals = nullptr; b->d_npts_global = nullptr; b->d_cache = nullptr;
-    b->d_hard_ids = nullptr; b->d_hard_cnt = nullptr; b->d_prob_ctr = nullptr;
+    void *ptrs[] = {b->d_probs, b->d_states, b->d_tasks, b->d_partials, b->d_hot, b->d_cold, b->d_totals,
+                    b->d_npts_global, b->d_hard_ids, b->d_hard_cnt, b->d_ndone, b->d_work, b->d_work_ctr};
     for (void *q : ptrs)
         if (q) cudaFreeAsync(q, st);
-    b->d_probs = nullptr; b->d_states = nullptr; b->d_tasks = nullptr; b->d_partials = nullptr; b->d_corr = nullptr;
+    b->d_probs = nullptr; b->d_states = nullptr; b->d_tasks = nullptr; b->d_partials = nullptr;
+    b->d_hot = nullptr; b->d_cold = nullptr; b->d_totals = nullptr; b->d_npts_global = nullptr;
+    b->d_hard_ids = nullptr; b->d_hard_cnt = nullptr; b->d_ndone = nullptr; b->d_work = nullptr;
+    b->d_work_ctr = nullptr;
     b->P = 0; b->nblk = 0; b->probs.clear();
 }
 
@@ -1170,6 +1158,7 @@ static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int
     const int n = b->cloud_off[ncloud];
     if (n >= (1 << kSubShift)) return VB200_ERR_INVALID;  // 2^28 source points per batch
     b->npts = n;
+    b->cloud_sphere.assign(4 * (size_t)std::max(ncloud, 1), 0.0);
     VB_CUDA(cudaMallocAsync((void **)&b->d_cloud_off, sizeof(int) * ((size_t)ncloud + 1), st));
     VB_CUDA(cudaMemcpyAsync(b->d_cloud_off, b->cloud_off.data(), sizeof(int) * ((size_t)ncloud + 1),
                             cudaMemcpyHostToDevice, st));
@@ -1178,12 +1167,14 @@ static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int
     if (n == 0) return VB200_OK;
     DevBuf<double> d_in(st);
     DevBuf<int> d_key(st), d_counts(st), d_start(st), d_sidx(st);
+    DevBuf<unsigned long long> d_bounds(st);  // per cloud: 6 bbox words + 1 radius word
     const size_t nb = (size_t)ncloud * kBuckets + 1;
     VB_CUDA(d_in.alloc(3 * (size_t)n));
     VB_CUDA(d_key.alloc((size_t)n));
     VB_CUDA(d_sidx.alloc((size_t)n));
     VB_CUDA(d_counts.alloc(nb));
     VB_CUDA(d_start.alloc(nb));
+    VB_CUDA(d_bounds.alloc(7 * (size_t)ncloud));
     VB_CUDA(cudaMemcpyAsync(d_in.p, src_xyz + 3 * off[0], sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
     VB_CUDA(cudaMemsetAsync(d_counts.p, 0, sizeof(int) * nb, st));
     const double inv_half = 2.0 / sc->grid.p.cell;
@@ -1196,16 +1187,42 @@ static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int
     k_src_list_buckets<<<div_up((int64_t)nb - 1, 256), 256, 0, st>>>((int)nb - 1, d_start.p, d_key.p, d_counts.p);
     k_src_sort_buckets<<<kNumSMsB200 * 8, 256, 0, st>>>(d_key.p, d_counts.p, d_start.p, d_sidx.p);
     k_src_gather<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, d_sidx.p, b->d_cloud_off, ncloud, b->d_src, b->d_src_orig);
+    // bounding sphere of every cloud: min words start at all-ones, max and radius words at zero
+    VB_CUDA(cudaMemsetAsync(d_bounds.p, 0, sizeof(unsigned long long) * 7 * (size_t)ncloud, st));
+    for (int c = 0; c < ncloud; c++)
+        VB_CUDA(cudaMemsetAsync(d_bounds.p + 6 * (size_t)c, 0xff, sizeof(unsigned long long) * 3, st));
+    k_cloud_bbox<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, b->d_cloud_off, ncloud, d_bounds.p);
+    k_cloud_radius<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, b->d_cloud_off, ncloud, d_bounds.p,
+                                                   d_bounds.p + 6 * (size_t)ncloud);
     VB_CUDA(cudaGetLastError());
-    b->launches += 5 + 3;
+    std::vector<unsigned long long> hb(7 * (size_t)ncloud);
+    VB_CUDA(cudaMemcpyAsync(hb.data(), d_bounds.p, sizeof(unsigned long long) * hb.size(), cudaMemcpyDeviceToHost, st));
+    b->launches += 5 + 3 + 2;
     VB_CUDA(cudaStreamSynchronize(st));  // temporaries are released on return
+    for (int c = 0; c < ncloud; c++) {
+        if (b->cloud_off[c + 1] == b->cloud_off[c]) continue;
+        double r2;
+        memcpy(&r2, &hb[6 * (size_t)ncloud + c], sizeof(r2));
+        for (int a = 0; a < 3; a++)
+            b->cloud_sphere[4 * (size_t)c + a] = 0.5 * (from_ordered_bits(hb[6 * (size_t)c + a]) + from_ordered_bits(hb[6 * (size_t)c + 3 + a]));
+        b->cloud_sphere[4 * (size_t)c + 3] = sqrt(r2) * (1.0 + 1e-12);
+    }
     return VB200_OK;
 }
 
-static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *init_T, int P) {
+static int batch_set_problems_impl(Batch *b, const int32_t *cloud_ids, const double *init_T, int P) {
     cudaStream_t st = b->stream;
-    batch_free_problems(b);
-    b->P = P;
+    // validate everything before touching the batch: a bad argument leaves the previous problems intact
+    {
+        int64_t total = 0;
+        for (int p = 0; p < P; p++) {
+            const int c = cloud_ids ? cloud_ids[p] : p;
+            if (c < 0 || c >= b->ncloud) return VB200_ERR_INVALID;
+            total += b->cloud_off[c + 1] - b->cloud_off[c];
+            if (total > 0x7fffffff) return VB200_ERR_INVALID;
+        }
+    }
+    batch_free_problems(b);  // P = 0 from here until every upload below has succeeded
     b->iter_base = 0;
     b->probs.resize((size_t)P);
     std::vector<BlockTask> tasks;
@@ -1213,13 +1230,14 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
     int64_t corr = 0;
     for (int p = 0; p < P; p++) {
         int c = cloud_ids ? cloud_ids[p] : p;
-        if (c < 0 || c >= b->ncloud) return VB200_ERR_INVALID;
         ProbDesc &pd = b->probs[p];
         pd.cloud = c;
         pd.npts = b->cloud_off[c + 1] - b->cloud_off[c];
         pd.src_begin = b->cloud_off[c];
         pd.corr_begin = (int)corr;
         pd.blk_begin = (int)tasks.size();
+        for (int a = 0; a < 3; a++) pd.ctr[a] = b->cloud_sphere[4 * (size_t)c + a];
+        pd.rad = b->cloud_sphere[4 * (size_t)c + 3];
         for (int s = 0; s < pd.npts; s += kChunk) {
             BlockTask t;
             t.prob = p;
@@ -1230,129 +1248,146 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
         }
         pd.blk_count = (int)tasks.size() - pd.blk_begin;
         corr += pd.npts;
-        if (corr > 0x7fffffff) return VB200_ERR_INVALID;
         ProbState &s = states[p];
         memset(&s, 0, sizeof(s));
         for (int i = 0; i < 16; i++) s.T[i] = init_T[16 * (size_t)p + i];
+        s.last_move = 1e30f;  // nothing is "settling" before the first update
     }
     b->nblk = (int)tasks.size();
     b->ncorr_slots = corr;
-    // Fusing the iteration tail into part B (its last warp per problem reduces + solves) was measured SLOWER
-    // than a separate k_solve launch: one warp summing ~800 partial rows is latency-bound (~50 us vs ~25 us).
-    // The code path stays for experiments (-DVB_FUSE_SOLVE).
-#ifdef VB_FUSE_SOLVE
-    b->all_nonempty = P > 0;
-    for (int p = 0; p < P; p++) b->all_nonempty = b->all_nonempty && b->probs[p].npts > 0;
-#else
-    b->all_nonempty = false;
-#endif
-    VB_CUDA(cudaMallocAsync((void **)&b->d_probs, sizeof(ProbDesc) * (size_t)std::max(P, 1), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_states, sizeof(ProbState) * (size_t)std::max(P, 1), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_tasks, sizeof(BlockTask) * (size_t)std::max(b->nblk, 1), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_partials, sizeof(double) * kPart * kRowsPerBlock * (size_t)std::max(b->nblk, 1), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_corr, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
+    const size_t nslot = (size_t)std::max<int64_t>(corr, 1), nblk1 = (size_t)std::max(b->nblk, 1), P1 = (size_t)std::max(P, 1);
+    VB_CUDA(cudaMallocAsync((void **)&b->d_probs, sizeof(ProbDesc) * P1, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_states, sizeof(ProbState) * P1, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_tasks, sizeof(BlockTask) * nblk1, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_partials, sizeof(double) * kPart * kRowsPerBlock * nblk1, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_hot, sizeof(HotRec) * nslot, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_cold, sizeof(ColdRec) * nslot, st));
     if (P) {
         VB_CUDA(cudaMemcpyAsync(b->d_probs, b->probs.data(), sizeof(ProbDesc) * (size_t)P, cudaMemcpyHostToDevice, st));
         VB_CUDA(cudaMemcpyAsync(b->d_states, states.data(), sizeof(ProbState) * (size_t)P, cudaMemcpyHostToDevice, st));
     }
     if (b->nblk)
         VB_CUDA(cudaMemcpyAsync(b->d_tasks, tasks.data(), sizeof(BlockTask) * (size_t)b->nblk, cudaMemcpyHostToDevice, st));
-    VB_CUDA(cudaMemsetAsync(b->d_corr, 0xff, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_cache, sizeof(NNCache) * (size_t)std::max<int64_t>(corr, 1), st));
-    VB_CUDA(cudaMemsetAsync(b->d_cache, 0xff, sizeof(NNCache) * (size_t)std::max<int64_t>(corr, 1), st));  // NaN
-    VB_CUDA(cudaMallocAsync((void **)&b->d_second, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
-    VB_CUDA(cudaMemsetAsync(b->d_second, 0xff, sizeof(int) * (size_t)std::max<int64_t>(corr, 1), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_hard_ids, (size_t)kChunk * (size_t)std::max(b->nblk, 1), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_hard_cnt, sizeof(int) * kPassWarps * (size_t)std::max(b->nblk, 1), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_prob_ctr, sizeof(int) * (size_t)std::max(P, 1), st));
-    VB_CUDA(cudaMemsetAsync(b->d_prob_ctr, 0, sizeof(int) * (size_t)std::max(P, 1), st));
+    // 0xff: c = -1 (no match, no candidates), limits NaN (every test compares false): knows nothing
+    VB_CUDA(cudaMemsetAsync(b->d_hot, 0xff, sizeof(HotRec) * nslot, st));
+    VB_CUDA(cudaMemsetAsync(b->d_cold, 0xff, sizeof(ColdRec) * nslot, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_hard_ids, (size_t)kChunk * nblk1, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_hard_cnt, sizeof(int) * kPassWarps * nblk1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_ndone, sizeof(int), st));
     VB_CUDA(cudaMemsetAsync(b->d_ndone, 0, sizeof(int), st));
-#ifdef VB_PB_WORKLIST
-    VB_CUDA(cudaMallocAsync((void **)&b->d_work, sizeof(int) * (size_t)std::max(b->nblk, 1), st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_work, sizeof(int) * nblk1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_work_ctr, sizeof(int) * 4, st));
     VB_CUDA(cudaMemsetAsync(b->d_work_ctr, 0, sizeof(int) * 4, st));
     b->pass_parity = 0;
-#endif
     VB_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
+    b->P = P;
     return VB200_OK;
 }
 
+static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *init_T, int P) {
+    const int rc = batch_set_problems_impl(b, cloud_ids, init_T, P);
+    // a failed set-up (CUDA error half-way) must not leave a batch that later launches on null buffers
+    if (rc != VB200_OK && rc != VB200_ERR_INVALID) batch_free_problems(b);
+    return rc;
+}
 
-// one correspondence pass = part A (every point, streaming) + part B (the points that need a search).  With
-// `sp` given, part B also finishes the iteration (reduction + estimator step by each problem's last warp).
-static void launch_pass(Batch *b, bool plane, const PassParams &pp_in, const SolveParams *sp = nullptr, int pass_index = 0) {
+// A kernel launch chained to the previous one on the stream by programmatic dependent launch (the kernels call
+// pdl_wait() before touching anything the previous kernel wrote), optionally as clusters of `cluster` blocks.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chained(void (*kernel)(KArgs...), int grid, int block, int cluster, cudaStream_t st,
+                                  Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)block, 1, 1);
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+    if (cluster > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = (unsigned)cluster;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        na++;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = (unsigned)na;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// one correspondence pass = part A (every point, streaming) + part B (the points that need a search)
+static int launch_pass(Batch *b, bool plane, const PassParams &pp_in) {
     Scene *sc = b->scene;
     cudaStream_t st = b->stream;
-#ifdef VB_PB_WORKLIST
     PassParams pp = pp_in;
     pp.work = b->d_work;
     pp.work_ctr = b->d_work_ctr;
     pp.parity = b->pass_parity;
     b->pass_parity ^= 1;
-    (void)sp; (void)pass_index;
-    const int nwarps = std::min(b->nblk * kPassWarps, kNumSMsB200 * 4 * VB_PASS_MINBLOCKS);
+    const int nwarps = std::min(b->nblk * kPassWarps, kNumSMsB200 * kPassWarps * VB_PASS_MINBLOCKS);
+    const int nb_b = div_up(nwarps, kPassWarps);
     if (plane) {
-        k_pass_a<1><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
-                                                  b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp);
-        k_pass_b_wl<1><<<nwarps, 32, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
-                                              b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp);
+        VB_CUDA(launch_chained(k_pass_a<1>, b->nblk, kPassTpb, 1, st, sc->grid, (const double *)b->d_src,
+                               (const BlockTask *)b->d_tasks, (const ProbState *)b->d_states, b->d_partials, b->d_hot,
+                               b->d_cold, b->d_hard_ids, b->d_hard_cnt, pp));
+        VB_CUDA(launch_chained(k_pass_b_wl<1>, nb_b, kPassTpb, 1, st, sc->grid, (const double *)b->d_src,
+                               (const BlockTask *)b->d_tasks, (const ProbState *)b->d_states, b->d_partials, b->d_hot,
+                               b->d_cold, (const unsigned char *)b->d_hard_ids, (const int *)b->d_hard_cnt, pp));
     } else {
-        k_pass_a<0><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
-                                                  b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp);
-        k_pass_b_wl<0><<<nwarps, 32, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
-                                              b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp);
+        VB_CUDA(launch_chained(k_pass_a<0>, b->nblk, kPassTpb, 1, st, sc->grid, (const double *)b->d_src,
+                               (const BlockTask *)b->d_tasks, (const ProbState *)b->d_states, b->d_partials, b->d_hot,
+                               b->d_cold, b->d_hard_ids, b->d_hard_cnt, pp));
+        VB_CUDA(launch_chained(k_pass_b_wl<0>, nb_b, kPassTpb, 1, st, sc->grid, (const double *)b->d_src,
+                               (const BlockTask *)b->d_tasks, (const ProbState *)b->d_states, b->d_partials, b->d_hot,
+                               b->d_cold, (const unsigned char *)b->d_hard_ids, (const int *)b->d_hard_cnt, pp));
     }
     b->launches += 2;
-    return;
-#else
-    const PassParams &pp = pp_in;
-#endif
-    SolveParams s0;
-    memset(&s0, 0, sizeof(s0));
-    const SolveParams &s = sp ? *sp : s0;
-    const int fuse = sp ? 1 : 0;
-    if (plane) {
-        k_pass_a<1><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
-                                                  b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp);
-        k_pass_b<1><<<b->nblk * kPassWarps, 32, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials,
-                                                         b->d_corr, b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp,
-                                                         b->d_probs, b->d_prob_ctr, s, pass_index, fuse);
-    } else {
-        k_pass_a<0><<<b->nblk, kPassTpb, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials, b->d_corr,
-                                                  b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp);
-        k_pass_b<0><<<b->nblk * kPassWarps, 32, 0, st>>>(sc->grid, b->d_src, b->d_tasks, b->d_states, b->d_partials,
-                                                         b->d_corr, b->d_cache, b->d_second, b->d_hard_ids, b->d_hard_cnt, pp,
-                                                         b->d_probs, b->d_prob_ctr, s, pass_index, fuse);
+    return VB200_OK;
+}
+
+static int launch_solve(Batch *b, const SolveParams &sp, int pass_index) {
+    VB_CUDA(launch_chained(k_solve, b->P * kSolveCtas, 256, kSolveCtas, b->stream, (const ProbDesc *)b->d_probs,
+                           b->d_states, (const double *)b->d_partials, sp, pass_index));
+    b->launches++;
+    return VB200_OK;
+}
+
+static int make_params(Batch *b, int estimator, const double *gravity, double max_dist, PassParams *pp,
+                       SolveParams *sp) {
+    Scene *sc = b->scene;
+    if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY) return VB200_ERR_INVALID;
+    if (!(max_dist > 0.0)) return VB200_ERR_DISTANCE;
+    if (max_dist > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
+    if (estimator != VB200_EST_P2P && (!b->has_normals || !sc->has_normals)) return VB200_ERR_NORMALS;
+    *pp = make_pass_params(sc->grid.p, max_dist, b->use_cache);
+    memset(sp, 0, sizeof(*sp));
+    sp->ndone = nullptr;
+    sp->estimator = estimator;
+    sp->g[0] = 0.0; sp->g[1] = 1.0; sp->g[2] = 0.0;  // VISMA's gravity convention: +Y (src/annotation.cpp:43,84)
+    if (estimator == VB200_EST_P2PLANE_GRAVITY && gravity) {
+        double l = sqrt(gravity[0] * gravity[0] + gravity[1] * gravity[1] + gravity[2] * gravity[2]);
+        if (!(l > 0.0)) return VB200_ERR_INVALID;
+        for (int a = 0; a < 3; a++) sp->g[a] = gravity[a] / l;
     }
-    b->launches += 2;
+    return VB200_OK;
 }
 
 // Iterations [it_begin, it_end] of the loop (the whole loop is 0..max_iter): vb200_icp_run enqueues the first few
 // of one half of its clouds, uploads the other half meanwhile, then comes back for the rest.
 static int batch_run(Batch *b, int estimator, const double *gravity, double max_dist, double rel_fitness,
                      double rel_rmse, int max_iter, int it_begin = 0, int it_end = 0x7fffffff) {
-    Scene *sc = b->scene;
     cudaStream_t st = b->stream;
-    if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY || max_iter < 0) return VB200_ERR_INVALID;
-    if (!(max_dist > 0.0)) return VB200_ERR_DISTANCE;
-    if (max_dist > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
-    const bool plane = estimator != VB200_EST_P2P;
-    if (plane && (!b->has_normals || !sc->has_normals)) return VB200_ERR_NORMALS;
-    if (b->P == 0) return VB200_OK;
-    const PassParams pp = make_pass_params(sc->grid.p, max_dist);
+    if (max_iter < 0) return VB200_ERR_INVALID;
+    PassParams pp;
     SolveParams sp;
-    sp.ndone = nullptr;
+    VB_TRY(make_params(b, estimator, gravity, max_dist, &pp, &sp));
+    if (b->P == 0) return VB200_OK;
+    const bool plane = estimator != VB200_EST_P2P;
     sp.rel_fitness = rel_fitness;
     sp.rel_rmse = rel_rmse;
     sp.max_iter = max_iter;
-    sp.estimator = estimator;
-    sp.g[0] = 0.0; sp.g[1] = 1.0; sp.g[2] = 0.0;  // VISMA's gravity convention: +Y (src/annotation.cpp:43,84)
-    if (estimator == VB200_EST_P2PLANE_GRAVITY && gravity) {
-        double l = sqrt(gravity[0] * gravity[0] + gravity[1] * gravity[1] + gravity[2] * gravity[2]);
-        if (!(l > 0.0)) return VB200_ERR_INVALID;
-        for (int a = 0; a < 3; a++) sp.g[a] = gravity[a] / l;
-    }
     // With a live convergence test most runs finish long before max_iter (5-7 iterations on the BASELINE
     // workload): every fourth iteration the host looks at the finished-problems counter and stops enqueueing
     // passes that would only find every problem done.
@@ -1365,34 +1400,10 @@ static int batch_run(Batch *b, int estimator, const double *gravity, double max_
             VB_CUDA(cudaStreamSynchronize(st));
             if (ndone >= b->P) break;
         }
-        if (b->all_nonempty) {
-            launch_pass(b, plane, pp, &sp, it);
-        } else {
-            // a problem without source points has no part-B warp to finish it: separate solve launch
-            if (b->nblk) launch_pass(b, plane, pp);
-            k_solve<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, b->d_hard_cnt, sp, it);
-            b->launches++;
-        }
+        if (b->nblk) VB_TRY(launch_pass(b, plane, pp));
+        VB_TRY(launch_solve(b, sp, it));
     }
     VB_CUDA(cudaGetLastError());
-    return VB200_OK;
-}
-
-static int make_params(Batch *b, int estimator, const double *gravity, double max_dist, PassParams *pp,
-                       SolveParams *sp) {
-    Scene *sc = b->scene;
-    if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY) return VB200_ERR_INVALID;
-    if (!(max_dist > 0.0)) return VB200_ERR_DISTANCE;
-    if (max_dist > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
-    if (estimator != VB200_EST_P2P && (!b->has_normals || !sc->has_normals)) return VB200_ERR_NORMALS;
-    *pp = make_pass_params(sc->grid.p, max_dist);
-    sp->estimator = estimator;
-    sp->g[0] = 0.0; sp->g[1] = 1.0; sp->g[2] = 0.0;
-    if (estimator == VB200_EST_P2PLANE_GRAVITY && gravity) {
-        double l = sqrt(gravity[0] * gravity[0] + gravity[1] * gravity[1] + gravity[2] * gravity[2]);
-        if (!(l > 0.0)) return VB200_ERR_INVALID;
-        for (int a = 0; a < 3; a++) sp->g[a] = gravity[a] / l;
-    }
     return VB200_OK;
 }
 
@@ -1401,7 +1412,6 @@ static int batch_pass(Batch *b, int estimator, double max_dist) {
     cudaStream_t st = b->stream;
     PassParams pp;
     SolveParams sp;
-    sp.ndone = nullptr;
     VB_TRY(make_params(b, estimator, nullptr, max_dist, &pp, &sp));
     if (b->P == 0) return VB200_OK;
     if (!b->d_totals && !b->d_totals_ext) {
@@ -1409,10 +1419,10 @@ static int batch_pass(Batch *b, int estimator, double max_dist) {
         VB_CUDA(cudaMemsetAsync(b->d_totals, 0, sizeof(double) * kAcc * (size_t)b->P, st));
     }
     double *totals = b->d_totals_ext ? b->d_totals_ext : b->d_totals;
-    if (b->nblk) {
-        launch_pass(b, estimator != VB200_EST_P2P, pp);
-    }
-    k_reduce<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, b->d_hard_cnt, estimator != VB200_EST_P2P, totals);
+    if (b->nblk) VB_TRY(launch_pass(b, estimator != VB200_EST_P2P, pp));
+    VB_CUDA(launch_chained(k_reduce, b->P * kSolveCtas, 256, kSolveCtas, st, (const ProbDesc *)b->d_probs,
+                           (const ProbState *)b->d_states, (const double *)b->d_partials,
+                           estimator != VB200_EST_P2P, totals));
     b->launches++;
     VB_CUDA(cudaGetLastError());
     return VB200_OK;
@@ -1424,7 +1434,6 @@ static int batch_solve(Batch *b, int estimator, const double *gravity, double ma
     cudaStream_t st = b->stream;
     PassParams pp;
     SolveParams sp;
-    sp.ndone = nullptr;
     VB_TRY(make_params(b, estimator, gravity, max_dist, &pp, &sp));
     sp.rel_fitness = rel_fitness;
     sp.rel_rmse = rel_rmse;
@@ -1436,49 +1445,34 @@ static int batch_solve(Batch *b, int estimator, const double *gravity, double ma
     std::vector<double> np((size_t)b->P);
     for (int p = 0; p < b->P; p++) np[p] = npts_global ? (double)npts_global[p] : (double)b->probs[p].npts;
     VB_CUDA(cudaMemcpyAsync(b->d_npts_global, np.data(), sizeof(double) * (size_t)b->P, cudaMemcpyHostToDevice, st));
-    k_solve_totals<<<div_up(b->P, 32), 32, 0, st>>>(b->P, b->d_states, totals, b->d_npts_global, sp, pass_index);
+    k_solve_totals<<<div_up(b->P, 32), 32, 0, st>>>(b->P, b->d_probs, b->d_states, totals, b->d_npts_global, sp, pass_index);
     b->launches++;
     VB_CUDA(cudaGetLastError());
     VB_CUDA(cudaStreamSynchronize(st));  // `np` is pageable host memory
     return VB200_OK;
 }
 
-// n unconditional iterations from the current transforms (no convergence test, `done` never set)
+// n unconditional iterations from the current transforms (no convergence test, `done` never set).  With
+// VB200_OPT_SPLIT_TIMING the pass and the solve of a single iteration are bracketed by events (which keeps the
+// solve from overlapping the pass's tail: a diagnostic, not the way the loop normally runs).
 static int batch_iterate(Batch *b, int estimator, const double *gravity, double max_dist, int n_iter) {
-    Scene *sc = b->scene;
     cudaStream_t st = b->stream;
-    if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY || n_iter < 0) return VB200_ERR_INVALID;
-    if (!(max_dist > 0.0)) return VB200_ERR_DISTANCE;
-    if (max_dist > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
-    const bool plane = estimator != VB200_EST_P2P;
-    if (plane && (!b->has_normals || !sc->has_normals)) return VB200_ERR_NORMALS;
-    if (b->P == 0 || b->nblk == 0) return VB200_OK;
-    const PassParams pp = make_pass_params(sc->grid.p, max_dist);
+    if (n_iter < 0) return VB200_ERR_INVALID;
+    PassParams pp;
     SolveParams sp;
-    sp.ndone = nullptr;
+    VB_TRY(make_params(b, estimator, gravity, max_dist, &pp, &sp));
+    if (b->P == 0 || b->nblk == 0) return VB200_OK;
+    const bool plane = estimator != VB200_EST_P2P;
     sp.rel_fitness = sp.rel_rmse = -1.0;  // |delta| < -1 never holds: no convergence exit
     sp.max_iter = 0x7fffffff;
-    sp.estimator = estimator;
-    sp.g[0] = 0.0; sp.g[1] = 1.0; sp.g[2] = 0.0;
-    if (estimator == VB200_EST_P2PLANE_GRAVITY && gravity) {
-        double l = sqrt(gravity[0] * gravity[0] + gravity[1] * gravity[1] + gravity[2] * gravity[2]);
-        if (!(l > 0.0)) return VB200_ERR_INVALID;
-        for (int a = 0; a < 3; a++) sp.g[a] = gravity[a] / l;
-    }
     for (int i = 0; i < 3; i++)
         if (!b->ev[i]) VB_CUDA(cudaEventCreate(&b->ev[i]));
-    const bool timed = n_iter == 1;  // per-kernel events only make sense around a single iteration
+    const bool timed = b->split_timing && n_iter == 1;  // per-kernel events only make sense around a single iteration
     for (int it = 0; it < n_iter; it++) {
         if (timed) VB_CUDA(cudaEventRecord(b->ev[0], st));
-        if (b->all_nonempty) {
-            launch_pass(b, plane, pp, &sp, b->iter_base++);
-            if (timed) VB_CUDA(cudaEventRecord(b->ev[1], st));
-        } else {
-            launch_pass(b, plane, pp);
-            if (timed) VB_CUDA(cudaEventRecord(b->ev[1], st));
-            k_solve<<<b->P, 256, 0, st>>>(b->d_probs, b->d_states, b->d_partials, b->d_hard_cnt, sp, b->iter_base++);
-            b->launches += 1;
-        }
+        VB_TRY(launch_pass(b, plane, pp));
+        if (timed) VB_CUDA(cudaEventRecord(b->ev[1], st));
+        VB_TRY(launch_solve(b, sp, b->iter_base++));
         if (timed) VB_CUDA(cudaEventRecord(b->ev[2], st));
     }
     b->ev_valid = timed;
@@ -1641,7 +1635,7 @@ extern "C" int vb200_batch_corr(vb200_batch_t *batch, int32_t p, int32_t *out_co
     vb::DevBuf<int> d_j(b->stream);
     if (pd.npts) {
         VB_CUDA(d_j.alloc((size_t)pd.npts));
-        vb::k_corr_orig<<<vb::div_up(pd.npts, 256), 256, 0, b->stream>>>(b->d_corr + pd.corr_begin, pd.npts,
+        vb::k_corr_orig<<<vb::div_up(pd.npts, 256), 256, 0, b->stream>>>(b->d_hot + pd.corr_begin, pd.npts,
                                                                                b->scene->grid.orig, d_j.p);
         VB_CUDA(cudaGetLastError());
         VB_CUDA(cudaMemcpyAsync(cj.data(), d_j.p, sizeof(int) * (size_t)pd.npts,
@@ -1772,17 +1766,41 @@ extern "C" int vb200_register_model_to_scene(vb200_scene_t *scan, const double *
     return VB200_OK;
 }
 
-extern "C" int vb200_estimate(const double *src_xyz, int64_t m, const double *tgt_xyz, const double *tgt_nrm,
-                              int64_t n, const int32_t *corr, int64_t K, int estimator, const double *gravity_axis,
-                              int device, double out_T[16]) {
-    if (!out_T || K < 0 || (K > 0 && (!src_xyz || !tgt_xyz || !corr))) return VB200_ERR_INVALID;
-    if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY) return VB200_ERR_INVALID;
-    for (int i = 0; i < 16; i++) out_T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+// shared tail of the estimator plug-in entries: reductions over K correspondences on `st`, then out17 =
+// {transformation (16), point-to-point rmse}.  corr == nullptr: rows are already gathered.
+static int estimate_on_device(const double *d_src, const double *d_tgt, const double *d_nrm, const int *d_corr,
+                              int64_t K, int estimator, const double *gravity_axis, cudaStream_t st, double out17[17]) {
+    vb::SolveParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.estimator = estimator;
+    sp.g[0] = 0.0; sp.g[1] = 1.0; sp.g[2] = 0.0;
+    if (estimator == VB200_EST_P2PLANE_GRAVITY && gravity_axis) {
+        double l = sqrt(gravity_axis[0] * gravity_axis[0] + gravity_axis[1] * gravity_axis[1] + gravity_axis[2] * gravity_axis[2]);
+        if (!(l > 0.0)) return VB200_ERR_INVALID;
+        for (int a = 0; a < 3; a++) sp.g[a] = gravity_axis[a] / l;
+    }
+    const int nblk = vb::div_up(K, vb::kChunk);
+    vb::DevBuf<double> d_part(st), d_out(st);
+    VB_CUDA(d_part.alloc((size_t)nblk * vb::kAcc));
+    VB_CUDA(d_out.alloc(17));
+    if (estimator != VB200_EST_P2P)
+        vb::k_estimate<1><<<nblk, vb::kPassTpb, 0, st>>>(d_src, d_tgt, d_nrm, d_corr, K, d_part.p);
+    else
+        vb::k_estimate<0><<<nblk, vb::kPassTpb, 0, st>>>(d_src, d_tgt, d_nrm, d_corr, K, d_part.p);
+    vb::k_estimate_solve<<<1, 256, 0, st>>>(d_part.p, nblk, d_src, d_corr, sp, d_out.p);
+    VB_CUDA(cudaGetLastError());
+    VB_CUDA(cudaMemcpyAsync(out17, d_out.p, sizeof(double) * 17, cudaMemcpyDeviceToHost, st));
+    VB_CUDA(cudaStreamSynchronize(st));
+    return VB200_OK;
+}
+
+// host clouds: marshal the K referenced rows (the reference gathers them too, TransformationEstimation.cpp:52-57)
+// and upload 72 bytes per correspondence instead of both clouds
+static int estimate_from_host(const double *src_xyz, int64_t m, const double *tgt_xyz, const double *tgt_nrm, int64_t n,
+                              const int32_t *corr, int64_t K, int estimator, const double *gravity_axis, int device,
+                              double out17[17]) {
     const bool plane = estimator != VB200_EST_P2P;
-    // corres.empty() || !target.HasNormals() -> Identity (TransformationEstimation.cpp:51,79-80)
-    if (K == 0 || (plane && !tgt_nrm)) return VB200_OK;
     VB_TRY(vb::select_device(device));
-    // marshal the K referenced rows (the reference gathers them too, TransformationEstimation.cpp:52-57)
     std::vector<double> h((size_t)K * 9);
     double *vs = h.data(), *vt = vs + 3 * K, *nt = vt + 3 * K;
     for (int64_t i = 0; i < K; i++) {
@@ -1794,41 +1812,77 @@ extern "C" int vb200_estimate(const double *src_xyz, int64_t m, const double *tg
             nt[3 * i + c] = plane ? tgt_nrm[3 * bq + c] : 0.0;
         }
     }
-    vb::SolveParams sp;
-    sp.ndone = nullptr;
-    sp.rel_fitness = sp.rel_rmse = 0.0;
-    sp.max_iter = 0;
-    sp.estimator = estimator;
-    sp.g[0] = 0.0; sp.g[1] = 1.0; sp.g[2] = 0.0;
-    if (estimator == VB200_EST_P2PLANE_GRAVITY && gravity_axis) {
-        double l = sqrt(gravity_axis[0] * gravity_axis[0] + gravity_axis[1] * gravity_axis[1] + gravity_axis[2] * gravity_axis[2]);
-        if (!(l > 0.0)) return VB200_ERR_INVALID;
-        for (int a = 0; a < 3; a++) sp.g[a] = gravity_axis[a] / l;
-    }
-    const int nblk = vb::div_up(K, vb::kChunk);
-    vb::DevBuf<double> d_in, d_part, d_T;
+    vb::DevBuf<double> d_in;
     VB_CUDA(d_in.alloc((size_t)K * 9));
-    VB_CUDA(d_part.alloc((size_t)nblk * vb::kAcc));
-    VB_CUDA(d_T.alloc(16));
     VB_CUDA(cudaMemcpy(d_in.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
-    if (plane)
-        vb::k_estimate<1><<<nblk, vb::kPassTpb>>>(d_in.p, d_in.p + 3 * K, d_in.p + 6 * K, K, d_part.p);
-    else
-        vb::k_estimate<0><<<nblk, vb::kPassTpb>>>(d_in.p, d_in.p + 3 * K, d_in.p + 6 * K, K, d_part.p);
-    vb::k_estimate_solve<<<1, 256>>>(d_part.p, nblk, d_in.p, sp, d_T.p);
-    VB_CUDA(cudaGetLastError());
-    VB_CUDA(cudaMemcpy(out_T, d_T.p, sizeof(double) * 16, cudaMemcpyDeviceToHost));
+    return estimate_on_device(d_in.p, d_in.p + 3 * K, d_in.p + 6 * K, nullptr, K, estimator, gravity_axis, nullptr, out17);
+}
+
+extern "C" int vb200_estimate(const double *src_xyz, int64_t m, const double *tgt_xyz, const double *tgt_nrm,
+                              int64_t n, const int32_t *corr, int64_t K, int estimator, const double *gravity_axis,
+                              int device, double out_T[16]) {
+    if (!out_T || K < 0 || (K > 0 && (!src_xyz || !tgt_xyz || !corr))) return VB200_ERR_INVALID;
+    if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY) return VB200_ERR_INVALID;
+    for (int i = 0; i < 16; i++) out_T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    // corres.empty() || !target.HasNormals() -> Identity (TransformationEstimation.cpp:51,79-80)
+    if (K == 0 || (estimator != VB200_EST_P2P && !tgt_nrm)) return VB200_OK;
+    double out17[17];
+    VB_TRY(estimate_from_host(src_xyz, m, tgt_xyz, tgt_nrm, n, corr, K, estimator, gravity_axis, device, out17));
+    memcpy(out_T, out17, sizeof(double) * 16);
     return VB200_OK;
+}
+
+extern "C" int vb200_estimate_device(const void *d_src_xyz, int64_t m, const void *d_tgt_xyz, const void *d_tgt_nrm,
+                                     int64_t n, const void *d_corr, int64_t K, int estimator,
+                                     const double *gravity_axis, int device, void *cuda_stream, double out_T[16]) {
+    if (!out_T || K < 0 || m < 0 || n < 0 || (K > 0 && (!d_src_xyz || !d_tgt_xyz || !d_corr))) return VB200_ERR_INVALID;
+    if (estimator < VB200_EST_P2P || estimator > VB200_EST_P2PLANE_GRAVITY) return VB200_ERR_INVALID;
+    for (int i = 0; i < 16; i++) out_T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    if (K == 0 || (estimator != VB200_EST_P2P && !d_tgt_nrm)) return VB200_OK;
+    VB_TRY(vb::select_device(device));
+    double out17[17];
+    VB_TRY(estimate_on_device((const double *)d_src_xyz, (const double *)d_tgt_xyz, (const double *)d_tgt_nrm,
+                              (const int *)d_corr, K, estimator, gravity_axis, (cudaStream_t)cuda_stream, out17));
+    memcpy(out_T, out17, sizeof(double) * 16);
+    return VB200_OK;
+}
+
+extern "C" int vb200_rmse(const double *src_xyz, int64_t m, const double *tgt_xyz, int64_t n, const int32_t *corr,
+                          int64_t K, int device, double *out_rmse) {
+    if (!out_rmse || K < 0 || (K > 0 && (!src_xyz || !tgt_xyz || !corr))) return VB200_ERR_INVALID;
+    *out_rmse = 0.0;  // corres.empty() -> 0 (src/constrained_ICP.cpp:17)
+    if (K == 0) return VB200_OK;
+    double out17[17];
+    VB_TRY(estimate_from_host(src_xyz, m, tgt_xyz, nullptr, n, corr, K, VB200_EST_P2P, nullptr, device, out17));
+    *out_rmse = out17[16];
+    return VB200_OK;
+}
+
+extern "C" int vb200_batch_set_option(vb200_batch_t *batch, int option, int value) {
+    if (!batch) return VB200_ERR_INVALID;
+    Batch *b = reinterpret_cast<Batch *>(batch);
+    switch (option) {
+        case VB200_OPT_NN_CACHE: b->use_cache = value != 0; return VB200_OK;
+        case VB200_OPT_SPLIT_TIMING: b->split_timing = value != 0; return VB200_OK;
+        default: return VB200_ERR_INVALID;
+    }
 }
 
 #ifdef VB_STATS
 // dev builds only (scripts/build_variants.sh ... "-DVB_STATS"): search-path counters of grid.cuh
 extern "C" int vb200_debug_stats(unsigned long long *out, int reset) {
-    if (out) cudaMemcpyFromSymbol(out, vb::g_stats, sizeof(unsigned long long) * 16);
+    if (out) cudaMemcpyFromSymbol(out, vb::g_stats, sizeof(unsigned long long) * 24);
     if (reset) {
-        unsigned long long z[16] = {0};
+        unsigned long long z[24] = {0};
         cudaMemcpyToSymbol(vb::g_stats, z, sizeof(z));
     }
+    return 0;
+}
+extern "C" int vb200_debug_states(vb200_batch_t *batch, float *cum, float *last_move) {
+    Batch *b = reinterpret_cast<Batch *>(batch);
+    std::vector<vb::ProbState> st((size_t)b->P);
+    cudaMemcpy(st.data(), b->d_states, sizeof(vb::ProbState) * (size_t)b->P, cudaMemcpyDeviceToHost);
+    for (int p = 0; p < b->P; p++) { cum[p] = st[p].cum; last_move[p] = st[p].last_move; }
     return 0;
 }
 #endif

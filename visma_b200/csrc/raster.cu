@@ -457,7 +457,9 @@ __global__ void __launch_bounds__(256) k_edge_mask(const unsigned *__restrict__ 
     if (p >= (int64_t)n_mesh * H * W) return;
     const int i = (int)(p % W), j = (int)((p / W) % H);
     const unsigned zc = z[p];
-    if (mask) mask[p] = zc != kZMax ? 255 : 0;
+    // the reference clears the colour buffer to 1.0 and reads GL_RED back (render/renderer.cpp:411-422): background =
+    // 255; its depth shader writes no colour, so covered pixels are undefined there — defined here as 0
+    if (mask) mask[p] = zc != kZMax ? 0 : 255;
     if (!edge) return;
     unsigned char e = 0;
     if (i >= 5 && i < W - 5 && j >= 5 && j < H - 5 && zc != kZMax) {

@@ -226,12 +226,8 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     VB_CUDA(d_hi.alloc((size_t)n));
     VB_CUDA(d_xyz.alloc(kPtStride * (size_t)n));
     VB_CUDA(d_orig.alloc((size_t)n));
-#ifdef VB_XYZN
-    double *const nrm_out = d_xyz.p + 3;  // the second half of every 48-byte record (left unwritten without normals)
-#else
     if (h_nrm) VB_CUDA(d_nrm.alloc(3 * (size_t)n));
     double *const nrm_out = d_nrm.p;
-#endif
     k_fine_starts<<<div_up(ncoarse, 128), 128, 0, st>>>((int)ncoarse, d_cstart.p, d_skey.p, d_cmask.p,
                                                          d_cbase.p, d_coarse.p, d_fstart.p, nfine, (int)n);
     VB_CUDA(cudaGetLastError());
@@ -244,11 +240,7 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     sc->grid.fstart = d_fstart.take();
     sc->grid.hi = d_hi.take();
     sc->grid.xyz = d_xyz.take();
-#ifdef VB_XYZN
-    sc->grid.nrm = h_nrm ? sc->grid.xyz + 3 : nullptr;
-#else
     sc->grid.nrm = h_nrm ? d_nrm.take() : nullptr;
-#endif
     sc->grid.orig = d_orig.take();
     sc->grid.n = n;
     return VB200_OK;
@@ -297,9 +289,7 @@ void scene_free(Scene *sc) {
     cudaFree((void *)sc->grid.fstart);
     cudaFree((void *)sc->grid.hi);
     cudaFree((void *)sc->grid.xyz);
-#ifndef VB_XYZN
     cudaFree((void *)sc->grid.nrm);
-#endif
     cudaFree((void *)sc->grid.orig);
     if (sc->stream2) cudaStreamDestroy(sc->stream2);
     if (sc->stream) cudaStreamDestroy(sc->stream);

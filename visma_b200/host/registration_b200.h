@@ -47,10 +47,46 @@ inline const double *Raw(const std::vector<Eigen::Vector3d> &v) {
     return v.empty() ? nullptr : reinterpret_cast<const double *>(v.data());
 }
 
+/// The gravity-constrained 4-DoF point-to-plane estimator (yaw about `gravity` + translation): the constraint
+/// the class name at include/constrained_ICP.h:14 promises and the reference never implemented (its 4DoF class is
+/// a copy of the point-to-point one).  An open3d::TransformationEstimation like any other: the reference's own
+/// CPU loop can drive it (ComputeTransformation runs on the GPU), and visma_b200::RegistrationICP recognises it
+/// and runs the whole loop on the GPU with VB200_EST_P2PLANE_GRAVITY.
+class TransformationEstimationPointToPlaneGravity : public open3d::TransformationEstimationPointToPlane {
+public:
+    explicit TransformationEstimationPointToPlaneGravity(const Eigen::Vector3d &gravity = Eigen::Vector3d(0, 1, 0),
+                                                         int device = 0)
+        : device_(device) {
+        gravity_[0] = gravity(0); gravity_[1] = gravity(1); gravity_[2] = gravity(2);  // +Y: src/annotation.cpp:43,84
+    }
+    Eigen::Matrix4d ComputeTransformation(const open3d::PointCloud &source, const open3d::PointCloud &target,
+                                          const open3d::CorrespondenceSet &corres) const override {
+        if (corres.empty() || !target.HasNormals()) return Eigen::Matrix4d::Identity();
+        std::vector<int32_t> c(2 * corres.size());
+        for (size_t i = 0; i < corres.size(); i++) { c[2 * i] = corres[i](0); c[2 * i + 1] = corres[i](1); }
+        double T[16];
+        int rc = vb200_estimate(Raw(source.points_), (int64_t)source.points_.size(), Raw(target.points_),
+                                Raw(target.normals_), (int64_t)target.points_.size(), c.data(), (int64_t)corres.size(),
+                                VB200_EST_P2PLANE_GRAVITY, gravity_, device_, T);
+        return rc == VB200_OK ? FromRowMajor(T) : Eigen::Matrix4d::Identity();
+    }
+    const double *gravity() const { return gravity_; }
+
+private:
+    double gravity_[3];
+    int device_;
+};
+
 inline int EstimatorKind(const open3d::TransformationEstimation &e) {
+    if (dynamic_cast<const TransformationEstimationPointToPlaneGravity *>(&e)) return VB200_EST_P2PLANE_GRAVITY;
     return e.GetTransformationEstimationType() == open3d::TransformationEstimationType::PointToPlane
                    ? VB200_EST_P2PLANE
                    : VB200_EST_P2P;
+}
+
+inline const double *GravityAxis(const open3d::TransformationEstimation &e) {
+    auto *g = dynamic_cast<const TransformationEstimationPointToPlaneGravity *>(&e);
+    return g ? g->gravity() : nullptr;
 }
 
 /// A target cloud resident on the GPU.  The reference rebuilds its KD-tree inside every RegistrationICP call
@@ -84,21 +120,31 @@ inline std::vector<open3d::RegistrationResult> RegistrationICPBatch(
     std::vector<open3d::RegistrationResult> out;
     for (int b = 0; b < B; b++) out.emplace_back(inits[b]);  // RegistrationResult(init), Registration.cpp:150,156
     if (B == 0) return out;
-    std::vector<int64_t> off(B + 1, 0);
-    bool normals = true;
+    // The reference decides per call (Registration.cpp:152-157): a point-to-plane problem whose source has no
+    // normals (an empty source never has, PointCloud.h:74-76) returns RegistrationResult(init) — that one only.
+    // Those sources are left out of the launch; the others run with `has normals` set.
+    const bool plane = EstimatorKind(estimation) != VB200_EST_P2P;
+    std::vector<int> run;  // positions in `sources` that go to the GPU
     for (int b = 0; b < B; b++) {
-        off[b + 1] = off[b] + (int64_t)sources[b]->points_.size();
-        normals = normals && sources[b]->HasNormals();
+        if (plane && !sources[b]->HasNormals())
+            open3d::PrintError("Error: TransformationEstimationPointToPlane requires pre-computed normal vectors.\n");
+        else
+            run.push_back(b);
     }
-    std::vector<double> xyz(3 * (size_t)off[B]), T0(16 * (size_t)B), T(16 * (size_t)B), fit(B), rmse(B);
-    for (int b = 0; b < B; b++) {
-        std::copy(Raw(sources[b]->points_), Raw(sources[b]->points_) + 3 * sources[b]->points_.size(),
-                  xyz.begin() + 3 * off[b]);
-        ToRowMajor(inits[b], T0.data() + 16 * b);
+    const int R = (int)run.size();
+    if (R == 0) return out;
+    std::vector<int64_t> off(R + 1, 0);
+    for (int k = 0; k < R; k++) off[k + 1] = off[k] + (int64_t)sources[run[k]]->points_.size();
+    std::vector<double> xyz(3 * (size_t)off[R] + 3), T0(16 * (size_t)R), T(16 * (size_t)R), fit(R), rmse(R);
+    for (int k = 0; k < R; k++) {
+        const open3d::PointCloud &s = *sources[run[k]];
+        if (!s.points_.empty()) std::copy(Raw(s.points_), Raw(s.points_) + 3 * s.points_.size(), xyz.begin() + 3 * off[k]);
+        ToRowMajor(inits[run[k]], T0.data() + 16 * k);
     }
-    std::vector<int32_t> nc(B), it(B), corr(2 * (size_t)off[B] + 2);
-    int rc = vb200_icp_run(target.handle(), xyz.data(), normals ? xyz.data() : nullptr, off.data(), B, T0.data(),
-                           EstimatorKind(estimation), nullptr, max_correspondence_distance,
+    std::vector<int32_t> nc(R), it(R), corr(2 * (size_t)off[R] + 2);
+    // only the PRESENCE of source normals matters below the ABI (the estimator reads the target's)
+    int rc = vb200_icp_run(target.handle(), xyz.data(), plane ? xyz.data() : nullptr, off.data(), R, T0.data(),
+                           EstimatorKind(estimation), GravityAxis(estimation), max_correspondence_distance,
                            criteria.relative_fitness_, criteria.relative_rmse_, criteria.max_iteration_, T.data(),
                            fit.data(), rmse.data(), nc.data(), it.data(), corr.data());
     if (rc == VB200_ERR_DISTANCE) {
@@ -113,13 +159,14 @@ inline std::vector<open3d::RegistrationResult> RegistrationICPBatch(
         open3d::PrintError("visma_b200: %s (%s)\n", vb200_strerror(rc), vb200_last_error());
         return out;
     }
-    for (int b = 0; b < B; b++) {
-        out[b].transformation_ = FromRowMajor(T.data() + 16 * b);
-        out[b].fitness_ = fit[b];
-        out[b].inlier_rmse_ = rmse[b];
-        out[b].correspondence_set_.resize(nc[b]);
-        for (int k = 0; k < nc[b]; k++)
-            out[b].correspondence_set_[k] = Eigen::Vector2i(corr[2 * (off[b] + k)], corr[2 * (off[b] + k) + 1]);
+    for (int k = 0; k < R; k++) {
+        open3d::RegistrationResult &r = out[run[k]];
+        r.transformation_ = FromRowMajor(T.data() + 16 * k);
+        r.fitness_ = fit[k];
+        r.inlier_rmse_ = rmse[k];
+        r.correspondence_set_.resize(nc[k]);
+        for (int j = 0; j < nc[k]; j++)
+            r.correspondence_set_[j] = Eigen::Vector2i(corr[2 * (off[k] + j)], corr[2 * (off[k] + j) + 1]);
     }
     return out;
 }
@@ -205,6 +252,18 @@ public:
     explicit TransformationEstimationPointToPoint4DoFB200(int device = 0) : device_(device) {}
     TransformationEstimationType GetTransformationEstimationType() const override {
         return TransformationEstimationType::PointToPoint;
+    }
+    /// src/constrained_ICP.cpp:13-23 on the GPU (vb200_rmse); the ICP loop itself never calls it
+    double ComputeRMSE(const PointCloud &source, const PointCloud &target,
+                       const CorrespondenceSet &corres) const override {
+        if (corres.empty()) return 0.0;
+        std::vector<int32_t> c(2 * corres.size());
+        for (size_t i = 0; i < corres.size(); i++) { c[2 * i] = corres[i][0]; c[2 * i + 1] = corres[i][1]; }
+        double rmse = 0.0;
+        int rc = vb200_rmse(visma_b200::Raw(source.points_), (int64_t)source.points_.size(),
+                            visma_b200::Raw(target.points_), (int64_t)target.points_.size(), c.data(),
+                            (int64_t)corres.size(), device_, &rmse);
+        return rc == VB200_OK ? rmse : TransformationEstimationPointToPoint4DoF::ComputeRMSE(source, target, corres);
     }
     Eigen::Matrix4d ComputeTransformation(const PointCloud &source, const PointCloud &target,
                                           const CorrespondenceSet &corres) const override {

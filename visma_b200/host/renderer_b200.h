@@ -33,6 +33,9 @@ public:
     void SetCamera(float z_near, float z_far, const float *intrinsics) {
         z_near_ = z_near; z_far_ = z_far;
         fx_ = intrinsics[0]; fy_ = intrinsics[1]; cx_ = intrinsics[2]; cy_ = intrinsics[3];
+        // the reference uploads view = vision_to_graphics here (render/renderer.cpp:270-276), which discards
+        // any pose set earlier: intrinsics first, pose second
+        pose_.setIdentity();
     }
     void SetCamera(float z_near, float z_far, float fx, float fy, float cx, float cy) {
         float k[4] = {fx, fy, cx, cy};
@@ -79,7 +82,8 @@ public:
     }
 
     /// RenderEdge / RenderMask (render/renderer.h:82-97): out = rows x cols bytes.  The edge pass linearises
-    /// depth with the shader's own fixed uniforms z_near = 0.05, z_far = 2.0 (render/renderer.cpp:95-96).
+    /// depth with the shader's own fixed uniforms z_near = 0.05, z_far = 2.0 (render/renderer.cpp:95-96).  The
+    /// mask keeps the reference's polarity: 255 on background (its clear colour, :411-422), 0 on the mesh.
     void RenderEdge(const Mat4fc &model, uint8_t *out) { EdgeMask(model, out, nullptr); }
     void RenderMask(const Mat4fc &model, uint8_t *out) { EdgeMask(model, nullptr, out); }
 

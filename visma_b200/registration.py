@@ -244,6 +244,10 @@ class Batch:
                                       criteria.relative_rmse_, criteria.max_iteration_, int(pass_index),
                                       None if n is None else _i64p(n)), "vb200_batch_solve")
 
+    def set_option(self, option, value):
+        """measurement knobs: _lib.OPT_NN_CACHE (0 = search every point every pass), _lib.OPT_SPLIT_TIMING"""
+        check(lib().vb200_batch_set_option(self._h, int(option), int(value)), "vb200_batch_set_option")
+
     def last_kernel_ms(self):
         a, b = C.c_float(), C.c_float()
         check(lib().vb200_batch_last_kernel_ms(self._h, C.byref(a), C.byref(b)), "vb200_batch_last_kernel_ms")
@@ -320,6 +324,29 @@ def ComputeTransformation(estimation, source, target, corres, device=0):
     T = np.zeros((4, 4))
     check(lib().vb200_estimate(_dp(s), len(s), _dp(t), _dp(tn), len(t), _ip(corr), len(corr),
                                estimation.kind, _dp(g), device, _dp(T)), "vb200_estimate")
+    return T
+
+
+def ComputeRMSE(source, target, corres, device=0):
+    """cicp::TransformationEstimationPointToPoint4DoF::ComputeRMSE (src/constrained_ICP.cpp:13-23) ==
+    TransformationEstimationPointToPoint::ComputeRMSE: sqrt(sum |s - t|^2 / K) on the GPU; 0 for an empty set."""
+    s = _f64(source.points_ if isinstance(source, PointCloud) else source)
+    t = _f64(target.points_ if isinstance(target, PointCloud) else target)
+    corr = np.ascontiguousarray(corres, np.int32).reshape(-1, 2)
+    out = C.c_double()
+    check(lib().vb200_rmse(_dp(s), len(s), _dp(t), len(t), _ip(corr), len(corr), device, C.byref(out)), "vb200_rmse")
+    return out.value
+
+
+def ComputeTransformationDevice(estimation, d_src, m, d_tgt, d_tgt_nrm, n, d_corr, K, device=0, stream=None):
+    """ComputeTransformation with every array already on the GPU (raw device pointers as ints): the rows are
+    gathered by the kernel (vb200_estimate_device)."""
+    g = getattr(estimation, "gravity_axis", None)
+    g = _f64(g) if g is not None else None
+    T = np.zeros((4, 4))
+    check(lib().vb200_estimate_device(C.c_void_p(d_src), int(m), C.c_void_p(d_tgt), C.c_void_p(d_tgt_nrm or None), int(n),
+                                      C.c_void_p(d_corr), int(K), estimation.kind, _dp(g), device,
+                                      C.c_void_p(stream or None), _dp(T)), "vb200_estimate_device")
     return T
 
 

@@ -30,11 +30,15 @@ class Renderer:
     def SetCamera(self, *args):
         """SetCamera(z_near, z_far, fx, fy, cx, cy) | SetCamera(z_near, z_far, intrinsics[4]) |
         SetCamera(pose 4x4, initial-camera -> current-camera)  (render/renderer.cpp:232-300)"""
-        if len(args) == 6:
-            self.z_near_, self.z_far_, self.fx_, self.fy_, self.cx_, self.cy_ = [float(a) for a in args]
-        elif len(args) == 3:
-            self.z_near_, self.z_far_ = float(args[0]), float(args[1])
-            self.fx_, self.fy_, self.cx_, self.cy_ = [float(a) for a in args[2]]
+        if len(args) in (6, 3):
+            if len(args) == 6:
+                self.z_near_, self.z_far_, self.fx_, self.fy_, self.cx_, self.cy_ = [float(a) for a in args]
+            else:
+                self.z_near_, self.z_far_ = float(args[0]), float(args[1])
+                self.fx_, self.fy_, self.cx_, self.cy_ = [float(a) for a in args[2]]
+            # the intrinsics overloads also upload view = vision_to_graphics (render/renderer.cpp:270-276),
+            # which discards any pose set before: a caller sets intrinsics first, pose second
+            self.pose_ = np.eye(4, dtype=np.float32).T.reshape(-1).copy()
         elif len(args) == 1:
             self.pose_ = np.asarray(args[0], np.float32).reshape(4, 4).T.reshape(-1).copy()  # to column-major
         else:
@@ -75,7 +79,8 @@ class Renderer:
         return self.RenderEdgeMaskBatch([model])[0][0]
 
     def RenderMask(self, model):
-        """RenderMask(model) -> H x W uint8, 255 where the mesh covers the pixel (render/renderer.cpp:403-433)."""
+        """RenderMask(model) -> H x W uint8 in the reference's polarity: 255 on background (the GL clear colour,
+        render/renderer.cpp:411-422), 0 where the mesh covers the pixel."""
         return self.RenderEdgeMaskBatch([model])[1][0]
 
     def RenderEdgeMaskBatch(self, models, meshes=None, edge_z_near=0.05, edge_z_far=2.0):
