@@ -46,3 +46,29 @@ def test_cpp_dropin_against_reference(tmp_path):
     assert r["errors"]["no_normals_fitness"] == 0
     assert r["voxel"]["n_ref"] == r["voxel"]["n_gpu"] and r["voxel"]["dsum"] < 1e-6
     assert r["render"]["covered"] > 10000 and abs(r["render"]["z_lin"] - 1.0) < 1e-3
+
+
+SHARDED = os.path.join(ROOT, "oracle", "_ref", "sharded_check")
+
+
+@pytest.mark.skipif(not os.path.exists(SHARDED), reason="oracle/_ref/sharded_check not built (needs /root/reference)")
+def test_cpp_sharded_host_path_equals_single_gpu(tmp_path):
+    """visma_b200::RegistrationICPSharded (C++ host, ncclAllGather of the 160-byte pose rows; SURVEY §8e) on the
+    GPUs this box has — two ranks when there are two devices, else one — against the single-GPU batch of all the
+    objects: identical transforms on every rank."""
+    d = small_scene(n_scene=120000, n_objects=5, m=5000, seed=31)
+    f = tmp_path / "in.bin"
+    with open(f, "wb") as fh:
+        np.array([len(d["scene_xyz"]), len(d["sources"]), 5000], np.int64).tofile(fh)
+        np.ascontiguousarray(d["scene_xyz"], np.float64).tofile(fh)
+        np.ascontiguousarray(d["scene_nrm"], np.float64).tofile(fh)
+        for p, n in d["sources"]:
+            np.ascontiguousarray(p, np.float64).tofile(fh)
+            np.ascontiguousarray(n, np.float64).tofile(fh)
+        np.ascontiguousarray(d["T_init"], np.float64).tofile(fh)
+    out = subprocess.run([SHARDED, str(f)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, (out.returncode, out.stderr[-2000:])
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("JSON:")][-1][5:])
+    assert r["objects"] == 5 and r["world"] >= 1
+    assert r["max_dT"] == 0 and r["max_dfit"] == 0 and r["ncorr_mismatches"] == 0
+    assert r["own_correspondence_sets_equal"] == 5 and r["fitness0"] > 0.9

@@ -36,7 +36,7 @@ def test_usage_and_config_errors(tmp_path):
     assert out.returncode == 1 and "failed to read file" in out.stderr
     (tmp_path / "bad.json").write_text('{"fx": 400, "translation": [0, 0, 1}')
     out = run_tool(tmp_path / "bad.json", tmp_path)
-    assert out.returncode == 1 and "json:" in out.stderr
+    assert out.returncode == 1 and "Line 1" in out.stderr   # jsoncpp's own diagnostics (the reference's parser)
     (tmp_path / "nomesh.json").write_text('{ // jsoncpp-style comment\n "mesh": "absent.obj", /* block */ "translation": [0, 0, 1]}')
     out = run_tool(tmp_path / "nomesh.json", tmp_path)
     assert out.returncode == 1 and "failed to load mesh absent.obj" in out.stderr

@@ -83,7 +83,8 @@ def lib():
     L.vb200_batch_launches.restype = C.c_int64
     L.vb200_batch_launches.argtypes = [vp]
     L.vb200_batch_iterate.argtypes = [vp, C.c_int, dp, C.c_double, C.c_int]
-    L.vb200_batch_set_option.argtypes = [vp, C.c_int, C.c_int]
+    if hasattr(L, "vb200_batch_set_option"):  # (absent only in older builds loaded through VISMA_B200_LIB for A/B)
+        L.vb200_batch_set_option.argtypes = [vp, C.c_int, C.c_int]
     L.vb200_batch_last_kernel_ms.argtypes = [vp, fp, fp]
     L.vb200_batch_pass.argtypes = [vp, C.c_int, C.c_double]
     L.vb200_batch_set_totals_buffer.argtypes = [vp, vp]
@@ -91,8 +92,9 @@ def lib():
     L.vb200_batch_totals.argtypes = [vp]
     L.vb200_batch_solve.argtypes = [vp, C.c_int, dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, i64p]
     L.vb200_estimate.argtypes = [dp, C.c_int64, dp, dp, C.c_int64, ip, C.c_int64, C.c_int, dp, C.c_int, dp]
-    L.vb200_estimate_device.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, C.c_int, dp, C.c_int, vp, dp]
-    L.vb200_rmse.argtypes = [dp, C.c_int64, dp, C.c_int64, ip, C.c_int64, C.c_int, dp]
+    if hasattr(L, "vb200_rmse"):
+        L.vb200_estimate_device.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, C.c_int, dp, C.c_int, vp, dp]
+        L.vb200_rmse.argtypes = [dp, C.c_int64, dp, C.c_int64, ip, C.c_int64, C.c_int, dp]
     L.vb200_register_model_to_scene.argtypes = [vp, dp, dp, C.c_int64, C.c_int, C.c_double, C.c_int, dp, ip, ip]
     L.vb200_render_depth_batch.argtypes = [fp, i64p, ip, i64p, C.c_int32, fp, fp, C.c_float, C.c_float,
                                            C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,

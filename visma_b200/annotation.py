@@ -104,6 +104,149 @@ def AnnotationTool(floor_points, scans, models, config, device=0, register=None)
     return out
 
 
+def AnnotationToolFromFiles(config, device=0, register=None, seed=0):
+    """feh::AnnotationTool(config) with its file IO (src/annotation.cpp:66-176): reads <dataroot>/<dataset>/
+    fragments/{floor.ply, objects.json, <entry>.ply} and <CAD_database_root>/<model>.obj, samples 2 x |scan| model
+    points per object (:126; seeded here, the reference seeds from the clock), runs the orientation-constrained
+    registration and writes fragments/alignment.json (key -> 3x4 row-major, :153,175).  Returns the dict."""
+    import os
+    from . import io3d
+    scene_dir = os.path.join(config["dataroot"], config["dataset"])
+    frag = os.path.join(scene_dir, "fragments")
+    floor, _ = io3d.read_ply(os.path.join(frag, "floor.ply"))
+    T0 = GravityAlignment(floor)
+    out = {}
+    for k, scan_name in enumerate(io3d.load_json(os.path.join(frag, "objects.json"))["entries"]):
+        model_name = scan_name[:scan_name.rfind("_")]
+        scan, _ = io3d.read_ply(os.path.join(frag, scan_name + ".ply"))
+        V, F = io3d.read_obj(os.path.join(config["CAD_database_root"], model_name + ".obj"))
+        n_scan = len(reg.VoxelDownSample(scan, config["ICP"]["voxel_size"], device).points_)
+        model = reg.SamplePointCloudFromMesh(V, F, 2 * n_scan, seed=seed + k, device=device)
+        Ttot, _ = AnnotateObject(scan, model, T0, config["ICP"], device, register)
+        out[scan_name] = Ttot[:3, :4].copy()
+    io3d.save_json({k: io3d.matrix_to_json(v) for k, v in out.items()}, os.path.join(frag, "alignment.json"))
+    return out
+
+
+def ComputeErrorMetric(errors):
+    """include/geometry.h:85-101 (median = element n >> 1 of the sorted errors)."""
+    e = np.asarray(errors, np.float64)
+    if len(e) == 0:
+        return dict(mean=float("nan"), std=float("nan"), median=float("nan"), min=float("inf"), max=float("-inf"))
+    mean = float(e.sum() / len(e))
+    return dict(mean=mean, std=float(np.sqrt(max((e * e).sum() / len(e) - mean * mean, 0.0))),
+                median=float(np.sort(e)[len(e) >> 1]), min=float(e.min()), max=float(e.max()))
+
+
+def MeasurePoseError(Gs, Gt, dist_thresh=0.5):
+    """include/geometry.h:147-180, as written: for every source pose the target poses are scanned for the nearest
+    translation below dist_thresh, and an error pair (translation distance, rotation angle of Rt^T Rs) is collected
+    INSIDE the scan — once per remaining target after the first match, each time against the best so far — so a
+    source matched early is counted several times.  Reproduced, since the reference's statistics include it.
+    Gs, Gt: lists of 3x4.  Returns (translation metric, rotation metric [rad])."""
+    t_err, r_err = [], []
+    for S in Gs:
+        best, idx = dist_thresh, -1
+        for j, T in enumerate(Gt):
+            dn = float(np.linalg.norm(T[:3, 3] - S[:3, 3]))
+            if dn < best:
+                best, idx = dn, j
+            if idx != -1:
+                dR = Gt[idx][:3, :3].T @ S[:3, :3]
+                w = 0.5 * np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]])
+                t_err.append(float(np.linalg.norm(Gt[idx][:3, 3] - S[:3, 3])))
+                r_err.append(float(np.arctan2(np.linalg.norm(w), (np.trace(dR) - 1.0) / 2.0)))  # AngleAxis(dR).angle()
+    return ComputeErrorMetric(t_err), ComputeErrorMetric(r_err)
+
+
+def _se3_log(T):
+    """6-vector (rho, phi) with exp(.) = T: SO(3) log by core/rodrigues.h:184-226 (invrodrigues), translation by V^-1."""
+    R, t = T[:3, :3], T[:3, 3]
+    c = 0.5 * (np.trace(R) - 1.0)
+    vee = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    if c > 1.0 - 1e-10:
+        w = 0.5 * vee
+    else:
+        th = np.arccos(max(c, -1.0))
+        w = th * 0.5 * vee / np.sin(th)
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-8:
+        Vinv = np.eye(3) - 0.5 * K + K @ K / 12.0
+    else:
+        Vinv = np.eye(3) - 0.5 * K + (1.0 / th ** 2 - (1.0 + np.cos(th)) / (2.0 * th * np.sin(th))) * K @ K
+    return np.concatenate([Vinv @ t, w])
+
+
+def _se3_exp(x):
+    rho, w = np.asarray(x[:3], np.float64), np.asarray(x[3:], np.float64)
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-8:
+        R = np.eye(3) + K + 0.5 * K @ K
+        V = np.eye(3) + 0.5 * K + K @ K / 6.0
+    else:
+        R = np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+        V = np.eye(3) + (1 - np.cos(th)) / th ** 2 * K + (th - np.sin(th)) / th ** 3 * K @ K
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = V @ rho
+    return T
+
+
+def OptimizeAlignment(tgt, src, matches, max_iter=100):
+    """feh::OptimizeAlignment (src/evaluation.cpp:43-77): the reference `throw`s here and keeps the intended
+    algorithm in a comment — an iteratively re-weighted mean of the relative poses dT_k = tgt_k * src_k^-1 in the
+    tangent space of SE(3): sum = sum_k w_k log(dT_k); T = exp(sum); w_k ~ 1 / max(1e-4, |log(tgt_k (T src_k)^-1)|),
+    normalised; stop when the sum changes by < 1e-5 relative; at most 100 iterations.  Implemented as written (in
+    double; the comment casts to float).  tgt / src: {id: 4x4 model_to_scene}; matches: [(src id, tgt id)]."""
+    if len(matches) == 0:
+        return np.eye(4)
+    w = np.full(len(matches), 1.0 / len(matches))
+    last = None
+    total = np.zeros(6)
+    for _ in range(max_iter):
+        total = np.zeros(6)
+        for k, (i, j) in enumerate(matches):
+            total += w[k] * _se3_log(tgt[j] @ np.linalg.inv(src[i]))
+        T = _se3_exp(total)
+        for k, (i, j) in enumerate(matches):
+            w[k] = 1.0 / max(1e-4, np.linalg.norm(_se3_log(tgt[j] @ np.linalg.inv(T @ src[i]))))
+        w /= w.sum()
+        if last is not None and np.linalg.norm(last - total) / max(np.linalg.norm(total), 1e-300) < 1e-5:
+            break
+        last = total
+    return _se3_exp(total)
+
+
+def FindCorrespondence(tgt, src, T_tgt_src, threshold):
+    """src/evaluation.cpp:18-41.  tgt / src: {id: (model_name, 4x4 model_to_scene)}; -> [(src id, tgt id)]."""
+    matches = []
+    for i, (_, Ts) in src.items():
+        best, best_j = threshold, -1
+        for j, (_, Tt) in tgt.items():
+            dT = np.linalg.inv(T_tgt_src @ Ts) @ Tt
+            n = float(np.linalg.norm(dT[:3, 3]))
+            if n < best:
+                best, best_j = n, j
+        if best_j >= 0:
+            matches.append((i, best_j))
+    return matches
+
+
+def RegisterScenes(tgt, src):
+    """src/evaluation.cpp:80-112 with the working OptimizeAlignment: -> (T_tgt_src 4x4, matches)."""
+    best = []
+    for i, (name_s, Ts) in src.items():
+        for j, (name_t, Tt) in tgt.items():
+            if name_s == name_t:
+                m = FindCorrespondence(tgt, src, Tt @ np.linalg.inv(Ts), 0.5)
+                if len(m) > len(best):
+                    best = m
+    T = OptimizeAlignment({j: T for j, (_, T) in tgt.items()}, {i: T for i, (_, T) in src.items()}, best)
+    return T, best
+
+
 def ICPRefinement(scene_points, model_clouds, model_to_scene, T_scene_src, options, device=0):
     """feh::ICPRefinement (src/evaluation.cpp:244-274): scene_est = union of the posed model samples
     (:250-256), scene voxel-down-sampled (:258), ONE RegistrationICP(scene_est -> scene) from T_scene_src

@@ -108,22 +108,25 @@ struct PassParams {
     float slack_lo, slack_hi;  // how far beyond the answer's reach a search of a settling problem looks (metric)
     float set_move;   // a problem whose latest update moved it by less than this is "settling": its searches keep sets
     int use_cache;    // 0: every point is searched in every pass (the ablation bench.py reports)
-    int *work;        // part-A blocks that listed anything in this pass, in order of arrival
-    int *work_ctr;    // [parity][2]: {blocks listed, part-B items handed out}; passes alternate between the two pairs
+    int *work;        // part B's work items of this pass — (block << 4 | batch) — in order of arrival
+    int *work_ctr;    // [parity][2]: {items listed, items handed out}; passes alternate between the two pairs
     int parity;
+    double *brows;    // per (block, batch): the batch's Gram matrix, until the block's last batch folds them
+    int *blk_done;    // per block: batches finished in this pass (reset by the one that folds)
 };
 
 #ifndef VB_SLACK_LO_PCT
-#define VB_SLACK_LO_PCT 8
+#define VB_SLACK_LO_PCT 1
 #endif
 #ifndef VB_SLACK_HI_PCT
-#define VB_SLACK_HI_PCT 30
+#define VB_SLACK_HI_PCT 20
 #endif
 #ifndef VB_SET_MOVE_PCT
-#define VB_SET_MOVE_PCT 60
+#define VB_SET_MOVE_PCT 20
 #endif
 #ifndef VB_SLACK_MOVE_PCT
-#define VB_SLACK_MOVE_PCT 50  // an alignment's updates shrink ~3-4x per iteration: everything still to come is < half the last one
+#define VB_SLACK_MOVE_PCT 100  // what is still to come moves a point by less than the last update did (updates shrink ~3-4x per
+                               // iteration), and its distance to the match can grow by as much again
 #endif
 inline PassParams make_pass_params(const GridParams &g, double max_dist, bool use_cache) {
     PassParams pp;
@@ -214,7 +217,7 @@ struct __align__(16) WarpScratch {
 };
 constexpr int kPart = 64;  // doubles per warp partial: the 8x8 Gram matrix of the staged rows
 static_assert(32 * kPtsPerThread <= 256, "hard_ids holds a warp's point ids in one byte");
-static_assert(kPassTpb == kPassWarps * 32 && kPassWarps * (kPart / 2) == kPassTpb, "k_pass_a zeroes part B's rows with one store per thread");
+static_assert(kPassTpb == kPassWarps * 32 && kChunk / 32 == 16, "work items are (block << 4 | batch)");
 
 // D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor cores (DMMA).  Lane l holds A[l>>2][l&3], B[l&3][l>>2] and
 // D[l>>2][2(l&3) + {0,1}].
@@ -331,7 +334,7 @@ struct PassCtx {
 #ifndef VB_PASS_A_MINBLOCKS
 #define VB_PASS_A_MINBLOCKS 12
 #endif
-constexpr int kRowsPerBlock = 1 + kPassWarps;  // partial rows per block: k_pass_a's (block total), then k_pass_b's warps
+constexpr int kBatchesPerBlock = kChunk / 32;  // a block's listed points form at most this many 32-point batches
 
 // sqrt(x) * (1 - 1e-6) + cum, every step rounded DOWN: the stored side of a cached-neighbour test
 __device__ __forceinline__ float lim_of(float sec, float cum) {
@@ -485,19 +488,23 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
     red[warp * 32 + lane] = mine;
     if (lane == 0) listed[warp] = nhard;
     __syncthreads();
-    double2 *out = reinterpret_cast<double2 *>(partials + (int64_t)blockIdx.x * kRowsPerBlock * kPart);
+    double2 *out = reinterpret_cast<double2 *>(partials + (int64_t)blockIdx.x * kPart);
     if (warp == 0) {
         double2 t = red[lane];
 #pragma unroll
         for (int w = 1; w < kPassWarps; w++) { t.x += red[w * 32 + lane].x; t.y += red[w * 32 + lane].y; }
         out[lane] = t;
     }
-    // nothing listed: part B never visits this block, so its rows are zeroed here
+    // the listed points, as 32-point batches, are part B's work items (one atomic per block that listed anything)
     int total = 0;
 #pragma unroll
     for (int w = 0; w < kPassWarps; w++) total += listed[w];
-    if (total == 0) out[(kPart / 2) + threadIdx.x] = make_double2(0.0, 0.0);  // 4 rows x 32 double2 = 128 threads
-    else if (threadIdx.x == 0) pp.work[atomicAdd(pp.work_ctr + 2 * pp.parity, 1)] = blockIdx.x;
+    if (total == 0) return;  // (block-uniform) part B never visits this block: its row is final
+    const int nb = (total + 31) >> 5;
+    __shared__ int base_sh;
+    if (threadIdx.x == 0) base_sh = atomicAdd(pp.work_ctr + 2 * pp.parity, nb);
+    __syncthreads();
+    if (threadIdx.x < nb) pp.work[base_sh + threadIdx.x] = (blockIdx.x << 4) | threadIdx.x;
 }
 
 // entry t of the 32 estimator slots from a summed 8x8 Gram matrix D.  Slot layout: point-to-plane 0..20 JTJ
@@ -524,11 +531,14 @@ __device__ __forceinline__ double slot_from_gram(const double *D, bool plane, in
 }
 
 // ---- pass, part B: the listed points, 32 searches at a time with every lane busy, over a worklist.  Part A
-// appends the blocks that listed anything (one atomic per such block); this is a resident grid whose WARPS each
-// take (block, warp) items off the list one at a time (an atomic per item: dynamic balance in an alignment's
-// first iterations, when every block is listed, and a near-empty launch once it has settled) until none is left.
-// Which warp handles an item is arbitrary; what it computes and where it writes — the item's own partial row,
-// the points' own records — is not, so the results do not depend on it.  Each search refreshes the point's records.
+// appends every listed block's batches — 32 of its listed points each — to the list (one atomic per such block);
+// this is a resident grid whose WARPS each take batches off the list one at a time (an atomic per batch: dynamic
+// balance whatever the number of objects on this GPU, and a near-empty launch once an alignment has settled).
+// Which warp handles a batch is arbitrary; what it computes and where it writes — the batch's own Gram row, the
+// points' own records — is not.  The last batch of a block to finish folds the block's rows into the block's
+// partial row in batch order: row = part A's + batch 0 + batch 1 + ..., the same association whatever ran where,
+// so the sums of an object do not depend on what else shares the GPU (the property sharding relies on), and
+// k_solve reads ONE row per block.  Each search refreshes the point's records.
 template <int MODE>
 __global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass_b_wl(
     GridDev G, const double *__restrict__ src_xyz, const BlockTask *__restrict__ tasks,
@@ -540,14 +550,15 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass_b_wl(
     pdl_launch_dependents();
     pdl_wait();  // part A has finished: the worklist and its length are final
     int *ctr = pp.work_ctr + 2 * pp.parity;
-    const int n_items = ctr[0] * kPassWarps;
+    const int n_items = ctr[0];
 #pragma unroll 1
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(ctr + 1, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        const int blk = pp.work[item / kPassWarps], warp = item % kPassWarps;
+        const int entry = pp.work[item];
+        const int blk = entry >> 4, k = entry & 15;
         int seg_end[kPassWarps];
         int total = 0;
 #pragma unroll
@@ -565,15 +576,14 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass_b_wl(
         const float last_move = st->last_move;
         const bool settling = last_move < pp.set_move;
         const float slack = settling ? fminf(fmaxf(last_move * (VB_SLACK_MOVE_PCT * 0.01f), pp.slack_lo), pp.slack_hi) : 0.0f;
-#pragma unroll 1
-        for (int h0 = 32 * warp; h0 < total; h0 += 32 * kPassWarps) {
-            const bool live = h0 + lane < total;
+        {
+            const int h = 32 * k + lane;
+            const bool live = h < total;
             double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             double vs[3] = {0, 0, 0}, d2 = 0.0;
             QueryCtx c;
             int prior = -1, slot = 0;
             if (live) {
-                const int h = h0 + lane;
                 int w = 0, base = 0;
 #pragma unroll
                 for (int i = 0; i < kPassWarps - 1; i++)
@@ -601,7 +611,28 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass_b_wl(
             }
             ctx.accumulate(ws.rows, x);
         }
-        ctx.write_partial(partials + ((int64_t)blk * kRowsPerBlock + 1 + warp) * kPart);
+        // the batch's row; then, if this was the block's last batch to finish, fold the block's rows in batch order
+        const int nb = (total + 31) >> 5;
+        double2 *brow = reinterpret_cast<double2 *>(pp.brows + ((int64_t)blk * kBatchesPerBlock) * kPart);
+        brow[k * (kPart / 2) + lane] = ctx.lane_pair();
+        __threadfence();
+        int prev = 0;
+        if (lane == 0) prev = atomicAdd(pp.blk_done + blk, 1);
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (prev == nb - 1) {
+            __threadfence();
+            if (lane == 0) pp.blk_done[blk] = 0;  // ready for the next pass
+            double2 *arow = reinterpret_cast<double2 *>(partials + (int64_t)blk * kPart);
+            double2 t = arow[lane];  // part A's row (the previous kernel's)
+            double2 v[kBatchesPerBlock];
+#pragma unroll
+            for (int j = 0; j < kBatchesPerBlock; j++)
+                v[j] = j < nb ? __ldcg(brow + j * (kPart / 2) + lane) : make_double2(0.0, 0.0);  // written by other SMs
+#pragma unroll
+            for (int j = 0; j < kBatchesPerBlock; j++)
+                if (j < nb) { t.x += v[j].x; t.y += v[j].y; }
+            arow[lane] = t;
+        }
         __syncwarp();
     }
 }
@@ -771,10 +802,10 @@ __device__ __forceinline__ double ld_dsmem_f64(const double *local_smem_ptr, uns
 __device__ __forceinline__ void cluster_reduce_partials(const ProbDesc &pd, const double *__restrict__ partials,
                                                         bool plane, double (*sw)[kPart], double *tot) {
     const unsigned rank = cluster_ctarank();
-    const int nrows = pd.blk_count * kRowsPerBlock;
+    const int nrows = pd.blk_count;  // one row per block (part B folds its batches' rows into it)
     const int per = (nrows + kSolveCtas - 1) / kSolveCtas;
     const int r0 = min((int)rank * per, nrows), r1 = min(r0 + per, nrows);
-    reduce_rows(partials + (int64_t)pd.blk_begin * kRowsPerBlock * kPart, r0, r1, sw);
+    reduce_rows(partials + (int64_t)pd.blk_begin * kPart, r0, r1, sw);
     cluster_sync_all();  // every block's sw[0] is final and visible cluster-wide
     if (rank == 0) {
         if (threadIdx.x < kPart) {
@@ -939,6 +970,11 @@ __host__ __device__ inline double from_ordered_bits(unsigned long long o) {
     return v;
 }
 
+__global__ void __launch_bounds__(256) k_cloud_bounds_init(unsigned long long *__restrict__ bounds, int ncloud) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 7 * ncloud) bounds[i] = (i < 6 * ncloud && i % 6 < 3) ? ~0ull : 0ull;
+}
+
 // bounds[c] = {min x, y, z, max x, y, z} as ordered bits (initialised to ~0 / 0 by the caller).  A warp whose
 // lanes all belong to one cloud (nearly every warp) reduces with shuffles and issues six atomics.
 __global__ void __launch_bounds__(256) k_cloud_bbox(const double *__restrict__ xyz, int n,
@@ -1090,6 +1126,10 @@ struct Batch {
     bool has_normals = false;
     bool use_cache = true;          // vb200_batch_set_option(VB200_OPT_NN_CACHE)
     bool split_timing = false;      // vb200_batch_set_option(VB200_OPT_SPLIT_TIMING)
+    // programmatic dependent launch between the kernels of an iteration.  Off when two batches run concurrently on
+    // two streams (vb200_icp_run's halves): a dependent grid that is resident early and waiting holds the registers
+    // the OTHER stream's kernels need (measured: 4.6 vs 4.1 ms per converging 32-object call)
+    bool chain = true;
     double *d_src = nullptr;        // sorted source points, 3*npts
     int *d_src_orig = nullptr;      // sorted position -> original index local to its cloud
     int *d_cloud_off = nullptr;
@@ -1107,8 +1147,10 @@ struct Batch {
     unsigned char *d_hard_ids = nullptr;     // per block and warp: the points part A left for part B
     int *d_hard_cnt = nullptr;
     int *d_ndone = nullptr;                  // problems finished since set_problems
-    int *d_work = nullptr;                   // part-A blocks with a non-empty list (k_pass_b_wl)
+    int *d_work = nullptr;                   // part B's work items: (block << 4 | batch)  (k_pass_b_wl)
     int *d_work_ctr = nullptr;               // 2 x {listed, handed out}
+    double *d_brows = nullptr;               // per (block, batch): the batch's Gram row until the block's rows are folded
+    int *d_blk_done = nullptr;               // per block: batches finished in the current pass
     int pass_parity = 0;
     int64_t launches = 0;
     int iter_base = 0;                       // running pass index for vb200_batch_iterate
@@ -1122,13 +1164,14 @@ struct Batch {
 static void batch_free_problems(Batch *b) {
     cudaStream_t st = b->stream;
     void *ptrs[] = {b->d_probs, b->d_states, b->d_tasks, b->d_partials, b->d_hot, b->d_cold, b->d_totals,
-                    b->d_npts_global, b->d_hard_ids, b->d_hard_cnt, b->d_ndone, b->d_work, b->d_work_ctr};
+                    b->d_npts_global, b->d_hard_ids, b->d_hard_cnt, b->d_ndone, b->d_work, b->d_work_ctr,
+                    b->d_brows, b->d_blk_done};
     for (void *q : ptrs)
         if (q) cudaFreeAsync(q, st);
     b->d_probs = nullptr; b->d_states = nullptr; b->d_tasks = nullptr; b->d_partials = nullptr;
     b->d_hot = nullptr; b->d_cold = nullptr; b->d_totals = nullptr; b->d_npts_global = nullptr;
     b->d_hard_ids = nullptr; b->d_hard_cnt = nullptr; b->d_ndone = nullptr; b->d_work = nullptr;
-    b->d_work_ctr = nullptr;
+    b->d_work_ctr = nullptr; b->d_brows = nullptr; b->d_blk_done = nullptr;
     b->P = 0; b->nblk = 0; b->probs.clear();
 }
 
@@ -1188,9 +1231,7 @@ static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int
     k_src_sort_buckets<<<kNumSMsB200 * 8, 256, 0, st>>>(d_key.p, d_counts.p, d_start.p, d_sidx.p);
     k_src_gather<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, d_sidx.p, b->d_cloud_off, ncloud, b->d_src, b->d_src_orig);
     // bounding sphere of every cloud: min words start at all-ones, max and radius words at zero
-    VB_CUDA(cudaMemsetAsync(d_bounds.p, 0, sizeof(unsigned long long) * 7 * (size_t)ncloud, st));
-    for (int c = 0; c < ncloud; c++)
-        VB_CUDA(cudaMemsetAsync(d_bounds.p + 6 * (size_t)c, 0xff, sizeof(unsigned long long) * 3, st));
+    k_cloud_bounds_init<<<div_up(7 * (int64_t)ncloud, 256), 256, 0, st>>>(d_bounds.p, ncloud);
     k_cloud_bbox<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, b->d_cloud_off, ncloud, d_bounds.p);
     k_cloud_radius<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, b->d_cloud_off, ncloud, d_bounds.p,
                                                    d_bounds.p + 6 * (size_t)ncloud);
@@ -1259,7 +1300,10 @@ static int batch_set_problems_impl(Batch *b, const int32_t *cloud_ids, const dou
     VB_CUDA(cudaMallocAsync((void **)&b->d_probs, sizeof(ProbDesc) * P1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_states, sizeof(ProbState) * P1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_tasks, sizeof(BlockTask) * nblk1, st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_partials, sizeof(double) * kPart * kRowsPerBlock * nblk1, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_partials, sizeof(double) * kPart * nblk1, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_brows, sizeof(double) * kPart * kBatchesPerBlock * nblk1, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_blk_done, sizeof(int) * nblk1, st));
+    VB_CUDA(cudaMemsetAsync(b->d_blk_done, 0, sizeof(int) * nblk1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_hot, sizeof(HotRec) * nslot, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_cold, sizeof(ColdRec) * nslot, st));
     if (P) {
@@ -1275,7 +1319,7 @@ static int batch_set_problems_impl(Batch *b, const int32_t *cloud_ids, const dou
     VB_CUDA(cudaMallocAsync((void **)&b->d_hard_cnt, sizeof(int) * kPassWarps * nblk1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_ndone, sizeof(int), st));
     VB_CUDA(cudaMemsetAsync(b->d_ndone, 0, sizeof(int), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_work, sizeof(int) * nblk1, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_work, sizeof(int) * kBatchesPerBlock * nblk1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_work_ctr, sizeof(int) * 4, st));
     VB_CUDA(cudaMemsetAsync(b->d_work_ctr, 0, sizeof(int) * 4, st));
     b->pass_parity = 0;
@@ -1295,16 +1339,18 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
 // pdl_wait() before touching anything the previous kernel wrote), optionally as clusters of `cluster` blocks.
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_chained(void (*kernel)(KArgs...), int grid, int block, int cluster, cudaStream_t st,
-                                  Args... args) {
+                                  bool chain, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
     cfg.blockDim = dim3((unsigned)block, 1, 1);
     cfg.stream = st;
     cudaLaunchAttribute at[2];
     int na = 0;
-    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[na].val.programmaticStreamSerializationAllowed = 1;
-    na++;
+    if (chain) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
     if (cluster > 1) {
         at[na].id = cudaLaunchAttributeClusterDimension;
         at[na].val.clusterDim.x = (unsigned)cluster;
@@ -1325,21 +1371,23 @@ static int launch_pass(Batch *b, bool plane, const PassParams &pp_in) {
     pp.work = b->d_work;
     pp.work_ctr = b->d_work_ctr;
     pp.parity = b->pass_parity;
+    pp.brows = b->d_brows;
+    pp.blk_done = b->d_blk_done;
     b->pass_parity ^= 1;
-    const int nwarps = std::min(b->nblk * kPassWarps, kNumSMsB200 * kPassWarps * VB_PASS_MINBLOCKS);
+    const int nwarps = std::min(b->nblk * kBatchesPerBlock, kNumSMsB200 * kPassWarps * VB_PASS_MINBLOCKS);
     const int nb_b = div_up(nwarps, kPassWarps);
     if (plane) {
-        VB_CUDA(launch_chained(k_pass_a<1>, b->nblk, kPassTpb, 1, st, sc->grid, (const double *)b->d_src,
+        VB_CUDA(launch_chained(k_pass_a<1>, b->nblk, kPassTpb, 1, st, b->chain, sc->grid, (const double *)b->d_src,
                                (const BlockTask *)b->d_tasks, (const ProbState *)b->d_states, b->d_partials, b->d_hot,
                                b->d_cold, b->d_hard_ids, b->d_hard_cnt, pp));
-        VB_CUDA(launch_chained(k_pass_b_wl<1>, nb_b, kPassTpb, 1, st, sc->grid, (const double *)b->d_src,
+        VB_CUDA(launch_chained(k_pass_b_wl<1>, nb_b, kPassTpb, 1, st, b->chain, sc->grid, (const double *)b->d_src,
                                (const BlockTask *)b->d_tasks, (const ProbState *)b->d_states, b->d_partials, b->d_hot,
                                b->d_cold, (const unsigned char *)b->d_hard_ids, (const int *)b->d_hard_cnt, pp));
     } else {
-        VB_CUDA(launch_chained(k_pass_a<0>, b->nblk, kPassTpb, 1, st, sc->grid, (const double *)b->d_src,
+        VB_CUDA(launch_chained(k_pass_a<0>, b->nblk, kPassTpb, 1, st, b->chain, sc->grid, (const double *)b->d_src,
                                (const BlockTask *)b->d_tasks, (const ProbState *)b->d_states, b->d_partials, b->d_hot,
                                b->d_cold, b->d_hard_ids, b->d_hard_cnt, pp));
-        VB_CUDA(launch_chained(k_pass_b_wl<0>, nb_b, kPassTpb, 1, st, sc->grid, (const double *)b->d_src,
+        VB_CUDA(launch_chained(k_pass_b_wl<0>, nb_b, kPassTpb, 1, st, b->chain, sc->grid, (const double *)b->d_src,
                                (const BlockTask *)b->d_tasks, (const ProbState *)b->d_states, b->d_partials, b->d_hot,
                                b->d_cold, (const unsigned char *)b->d_hard_ids, (const int *)b->d_hard_cnt, pp));
     }
@@ -1348,7 +1396,7 @@ static int launch_pass(Batch *b, bool plane, const PassParams &pp_in) {
 }
 
 static int launch_solve(Batch *b, const SolveParams &sp, int pass_index) {
-    VB_CUDA(launch_chained(k_solve, b->P * kSolveCtas, 256, kSolveCtas, b->stream, (const ProbDesc *)b->d_probs,
+    VB_CUDA(launch_chained(k_solve, b->P * kSolveCtas, 256, kSolveCtas, b->stream, b->chain, (const ProbDesc *)b->d_probs,
                            b->d_states, (const double *)b->d_partials, sp, pass_index));
     b->launches++;
     return VB200_OK;
@@ -1420,7 +1468,7 @@ static int batch_pass(Batch *b, int estimator, double max_dist) {
     }
     double *totals = b->d_totals_ext ? b->d_totals_ext : b->d_totals;
     if (b->nblk) VB_TRY(launch_pass(b, estimator != VB200_EST_P2P, pp));
-    VB_CUDA(launch_chained(k_reduce, b->P * kSolveCtas, 256, kSolveCtas, st, (const ProbDesc *)b->d_probs,
+    VB_CUDA(launch_chained(k_reduce, b->P * kSolveCtas, 256, kSolveCtas, st, b->chain, (const ProbDesc *)b->d_probs,
                            (const ProbState *)b->d_states, (const double *)b->d_partials,
                            estimator != VB200_EST_P2P, totals));
     b->launches++;
@@ -1699,6 +1747,7 @@ extern "C" int vb200_icp_run(vb200_scene_t *scene, const double *src_xyz, const 
     for (int h = 0; h < nhalf && rc == VB200_OK; h++) {
         const int p0 = first[h], np = first[h + 1] - first[h];
         rc = batch_create_on(scene, h == 0 ? nullptr : sc->stream2, src_xyz, src_nrm, src_offsets + p0, np, &half[h]);
+        if (rc == VB200_OK && nhalf == 2) reinterpret_cast<Batch *>(half[h])->chain = false;
         if (rc == VB200_OK) rc = vb200_batch_set_problems(half[h], nullptr, init_T + 16 * (size_t)p0, np);
         if (rc == VB200_OK)
             rc = vb::batch_run(reinterpret_cast<Batch *>(half[h]), estimator, gravity_axis, max_dist, rel_fitness,
