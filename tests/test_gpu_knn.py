@@ -164,6 +164,25 @@ def test_grid_search_equals_exhaustive_search_at_full_size(vb):
     assert (gi >= 0).sum() > 7000 and (gi < 0).sum() > 300
 
 
+def test_grid_search_equals_exhaustive_search_at_ten_million_points(vb, oracle):
+    """The largest size of BASELINE's KNN sweep (config 5: 10 M scene points x 10 000 queries): grid search vs the
+    exhaustive search bit for bit on all 10 000 queries, and both against the CPU oracle's exhaustive scan on 48 of
+    them (4.8e8 double distance evaluations)."""
+    d = vb.synth.make_room_scene(10_000_000, 8, 10)
+    tgt = d["scene_xyz"]
+    q = np.concatenate([vb.synth.knn_queries(tgt, 9000, sigma=0.01), vb.synth.knn_queries(tgt, 1000, sigma=0.08, seed=9)])
+    sc = vb.reg.Scene(tgt, 0.075)
+    gi, gd = sc.SearchHybrid1(q, 0.075)
+    bi, bd = vb.reg.SearchHybrid1BruteForce(tgt, q, 0.075)
+    assert (gi == bi).all() and (gd == bd).all()
+    assert (gi >= 0).sum() > 9000 and (gi < 0).sum() > 100
+    pick = np.r_[0:24, 9000:9024]
+    oi, od = oracle.knn1_brute(tgt, q[pick])
+    r2 = float(np.float32(0.075 * 0.075))
+    hit = od < r2
+    assert np.array_equal(np.where(hit, oi, -1), gi[pick]) and np.array_equal(np.where(hit, od, 0.0), gd[pick])
+
+
 def test_nan_points_are_never_neighbours(vb, oracle):
     """A NaN target or query point matches nothing (the reference's `dist < worst_dist` is false for NaN), in the
     grid search and in the exhaustive one, whatever the NaN's sign bit."""

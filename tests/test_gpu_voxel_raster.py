@@ -41,6 +41,24 @@ def test_render_depth_tool_config(vb, oracle):
         assert 0.6 < lin.min() and lin.max() < 1.5
 
 
+def test_render_depth_against_an_independent_pinhole_rasteriser__parity_unpinned_by_the_reference(vb):
+    """R5 rests on more than the restated GL pipeline: the GPU z-buffer against the float64 rasteriser derived from
+    the closed-form pinhole mapping (tests/indep_raster.py) — identical coverage away from triangle edges, depth
+    within a few 24-bit units (plus the 1/256-pixel snapping on steep triangles)."""
+    from indep_raster import compare, render_depth_indep
+    V, F = vb.synth.load_chair()
+    pose = vb.synth.make_T(vb.synth.rot_xyz(0.05, -0.1, 0.02), [0.03, 0.02, 0.1])
+    for cam, model, ps in ((dict(CAM, cy=400.0), vb.synth.make_T(np.eye(3), [0, 0, 1.0]), np.eye(4)),
+                           (CAM, vb.synth.make_T(vb.synth.rot_y(0.8), [0.2, -0.1, 1.6]), pose)):
+        r = gpu_renderer(vb, cam, ps)
+        r.SetMesh(V, F)
+        _, z24 = r.RenderDepthBatch([model], want_z24=True)
+        depth, covered, uncertain, slope = render_depth_indep(V, F, model, ps, cam["zn"], cam["zf"], cam["fx"], cam["fy"],
+                                                              cam["cx"], cam["cy"], cam["H"], cam["W"])
+        c = compare(z24[0], depth, covered, uncertain, slope)
+        assert c["n_covered"] > 5000 and c["coverage_mismatch_sure"] == 0 and c["depth_over_tol"] == 0, c
+
+
 def test_render_batch_poses(vb, oracle):
     V, F = vb.synth.load_chair()
     poses = vb.synth.render_poses(12)
