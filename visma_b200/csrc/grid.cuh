@@ -4,8 +4,8 @@
 //
 // Layout in HBM (all arrays in "sorted order": by coarse cell, then fine cell, then original index):
 //   hi   float4[N]  (x-ctr, y-ctr, z-ctr) rounded to f32, w = original index bits   16 B/pt  screening
-//   xyz  double[3N] exact coordinates                                              24 B/pt  decisions
-//   nrm  double[3N] exact normals (optional)                                       24 B/pt  estimator
+//   xyz  double[4N] exact coordinates, padded to one 32-byte sector                32 B/pt  decisions
+//   nrm  double[4N] exact normals (optional), likewise                             32 B/pt  estimator
 //   orig int[N]     sorted position -> original index                               4 B/pt
 //   coarse CoarseCell[ncoarse]  {64-bit occupancy mask of the 4x4x4 fine cells, base into fstart} 16 B
 //   fstart int[nfine+1]         start position of every OCCUPIED fine cell
@@ -42,15 +42,19 @@ struct GridParams {
     float band_a, band_b, band_rel;
 };
 
-constexpr int kPtStride = 3;  // doubles between consecutive scene points in `xyz` and in `nrm`
+// Doubles between consecutive scene points in `xyz` and in `nrm`: records are padded to 32 bytes, one aligned L2
+// sector each, and read with ONE 256-bit load (ld_rec).  With packed 24-byte records a gather cost three 8-byte
+// requests of up to 32 sectors each and half the records straddled two sectors: the L1 tag stage, not DRAM, was
+// what a settled correspondence pass saturated (l1tex throughput 63-74 % at 30 % of DRAM bandwidth).
+constexpr int kPtStride = 4;
 
 struct GridDev {
     GridParams p;
     const CoarseCell *coarse;
     const int *fstart;
     const float4 *hi;
-    const double *xyz;  // 3 doubles per point
-    const double *nrm;  // nullable; 3 doubles per point
+    const double *xyz;  // kPtStride doubles per point (x, y, z, 0)
+    const double *nrm;  // nullable; likewise
     const int *orig;
     int64_t n;
 };
@@ -71,8 +75,20 @@ __device__ __forceinline__ float band(const GridParams &g, float d32) {
 
 // flann::L2<double> on 3-D data: ((dx*dx) + dy*dy) + dz*dz with every operation rounded separately
 // (O3D/3rdparty/flann/algorithms/dist.h:150-177) — no FMA contraction so d2 is bit-identical to the CPU.
+// one scene record (x, y, z of a point or of a normal): a single 256-bit read-only load of its 32-byte sector
+struct Rec3 {
+    double x, y, z;
+};
+__device__ __forceinline__ Rec3 ld_rec(const double *__restrict__ rec) {
+    Rec3 r;
+    asm("{\n.reg .f64 pad;\nld.global.nc.v4.f64 {%0, %1, %2, pad}, [%3];\n}" : "=d"(r.x), "=d"(r.y), "=d"(r.z) : "l"(rec));
+    return r;
+}
+
+// t = a scene record (G.xyz + kPtStride * position)
 __device__ __forceinline__ double l2_exact(double qx, double qy, double qz, const double *__restrict__ t) {
-    double dx = __dsub_rn(qx, t[0]), dy = __dsub_rn(qy, t[1]), dz = __dsub_rn(qz, t[2]);
+    const Rec3 p = ld_rec(t);
+    double dx = __dsub_rn(qx, p.x), dy = __dsub_rn(qy, p.y), dz = __dsub_rn(qz, p.z);
     double r = __dmul_rn(dx, dx);
     r = __dadd_rn(r, __dmul_rn(dy, dy));
     r = __dadd_rn(r, __dmul_rn(dz, dz));
@@ -105,6 +121,13 @@ __device__ __forceinline__ bool make_query(const GridParams &g, double x, double
     c.fx = (float)(ux - fx); c.fy = (float)(uy - fy); c.fz = (float)(uz - fz);
     c.qx = (float)(x - g.ctr[0]); c.qy = (float)(y - g.ctr[1]); c.qz = (float)(z - g.ctr[2]);
     return true;
+}
+
+// make_query's range test alone
+__device__ __forceinline__ bool inside_grid(const GridParams &g, double x, double y, double z) {
+    const double ux = (x - g.lo[0]) * g.inv_fine, uy = (y - g.lo[1]) * g.inv_fine, uz = (z - g.lo[2]) * g.inv_fine;
+    return ux >= 0.0 && uy >= 0.0 && uz >= 0.0 && ux < (double)g.fdim[0] && uy < (double)g.fdim[1] &&
+           uz < (double)g.fdim[2];
 }
 
 // small non-negative int -> float without the (quarter-rate) I2F conversion unit
@@ -636,6 +659,7 @@ __device__ __forceinline__ Top5 top5_of_near(const GridDev &G, const QueryCtx &c
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // list the occupied fine cells with done < gap2 <= thr (squared distance to the query, deflated) as runs, in ONE
 // flat loop over the cells of the query's box (nested loops with per-lane trip counts serialise: measured 30 passes

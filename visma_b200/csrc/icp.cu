@@ -36,9 +36,12 @@ namespace {
 #ifndef VB_PASS_TPB
 #define VB_PASS_TPB 128
 #endif
-#ifndef VB_PASS_MINBLOCKS
-#define VB_PASS_MINBLOCKS (768 / VB_PASS_TPB)  // part B: 24 resident warps per SM -> 80 registers per thread
+#ifndef VB_PASS_B_TPB
+#define VB_PASS_B_TPB 128  // part B's block: independent warps (no block-level barrier), 24 resident per SM -> 80 registers
 #endif
+constexpr int kPassBTpb = VB_PASS_B_TPB;
+constexpr int kPassBWarps = kPassBTpb / 32;
+constexpr int kPassBBlocksPerSM = 768 / kPassBTpb;
 constexpr int kPassTpb = VB_PASS_TPB;
 constexpr int kPassWarps = kPassTpb / 32;  // every warp writes its own partial: no block-level barrier
 #ifndef VB_PASS_PTS
@@ -113,6 +116,7 @@ struct PassParams {
     int parity;
     double *brows;    // per (block, batch): the batch's Gram matrix, until the block's last batch folds them
     int *blk_done;    // per block: batches finished in this pass (reset by the one that folds)
+    int64_t src_n;    // points in the batch's source array (x[src_n], y[src_n], z[src_n])
 };
 
 #ifndef VB_SLACK_LO_PCT
@@ -217,7 +221,7 @@ struct __align__(16) WarpScratch {
 };
 constexpr int kPart = 64;  // doubles per warp partial: the 8x8 Gram matrix of the staged rows
 static_assert(32 * kPtsPerThread <= 256, "hard_ids holds a warp's point ids in one byte");
-static_assert(kPassTpb == kPassWarps * 32 && kChunk / 32 == 16, "work items are (block << 4 | batch)");
+static_assert(kPassTpb == kPassWarps * 32 && kChunk / 32 <= 16, "work items are (block << 4 | batch)");
 
 // D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor cores (DMMA).  Lane l holds A[l>>2][l&3], B[l&3][l>>2] and
 // D[l>>2][2(l&3) + {0,1}].
@@ -256,22 +260,20 @@ struct PassCtx {
 
     __device__ __forceinline__ PassCtx(const GridDev &g, const double *t) : G(g), T(t) {}
 
-    __device__ __forceinline__ void transform(const double *__restrict__ p, double (&vs)[3]) const {
-        const double px = p[0], py = p[1], pz = p[2];
+    // source point i of the batch's sorted clouds (x[n], y[n], z[n])
+    __device__ __forceinline__ void transform(const double *__restrict__ src, int64_t n, int64_t i, double (&vs)[3]) const {
+        const double px = src[i], py = src[n + i], pz = src[2 * n + i];
         vs[0] = T[0] * px + T[1] * py + T[2] * pz + T[3];
         vs[1] = T[4] * px + T[5] * py + T[6] * pz + T[7];
         vs[2] = T[8] * px + T[9] * py + T[10] * pz + T[11];
     }
 
-    // the exact decision for match candidate bs (>= 0) and, if accepted, the lane's estimator row
-    __device__ __forceinline__ bool row_of(int bs, const double (&vs)[3], double r2, double (&x)[8]) {
-        const double *t = G.xyz + kPtStride * (int64_t)bs;
-        const double vt[3] = {t[0], t[1], t[2]};
-        const double d2 = l2_exact(vs[0], vs[1], vs[2], vt);
+    // the exact decision for a match candidate at vt (normal nt) and, if accepted, the lane's estimator row
+    __device__ __forceinline__ bool row_from(const double (&vs)[3], const double (&vt)[3], const double (&nt)[3], double r2,
+                                             double (&x)[8]) {
+        const double d2 = l2_exact(vs[0], vs[1], vs[2], vt[0], vt[1], vt[2]);
         if (!(d2 < r2)) return false;
         if (MODE == 1) {
-            const double *nn = G.nrm + kPtStride * (int64_t)bs;
-            const double nt[3] = {nn[0], nn[1], nn[2]};
             x[0] = vs[1] * nt[2] - vs[2] * nt[1];
             x[1] = vs[2] * nt[0] - vs[0] * nt[2];
             x[2] = vs[0] * nt[1] - vs[1] * nt[0];
@@ -287,6 +289,17 @@ struct PassCtx {
         sum_d2 += d2;
         count += 1;
         return true;
+    }
+    // ... for match candidate bs (>= 0), gathered here: one 256-bit load per record
+    __device__ __forceinline__ bool row_of(int bs, const double (&vs)[3], double r2, double (&x)[8]) {
+        const Rec3 t = ld_rec(G.xyz + kPtStride * (int64_t)bs);
+        const double vt[3] = {t.x, t.y, t.z};
+        double nt[3] = {0.0, 0.0, 0.0};
+        if (MODE == 1) {
+            const Rec3 nn = ld_rec(G.nrm + kPtStride * (int64_t)bs);
+            nt[0] = nn.x; nt[1] = nn.y; nt[2] = nn.z;
+        }
+        return row_from(vs, vt, nt, r2, x);
     }
 
     // all 32 lanes: stage the rows (zeros for lanes without a match) and accumulate their Gram matrix
@@ -362,6 +375,61 @@ static __device__ __noinline__ int settle_set_exact(const GridDev &G, double qx,
     return w;
 }
 
+// Part A's second chance for a point whose single-candidate test failed: its candidate set (ColdRec).  Is the
+// nearest of the four nearer than anything outside the set can be?  Then the nearest neighbour is that member
+// (settled in double when f32 cannot order them); the records are refreshed.  Returns the match or -1.
+static __device__ __forceinline__ int settle_from_set(const GridDev &G, const PassParams &pp, double qx, double qy, double qz,
+                                                   int c0, int slot, float cum, float cum_eps, HotRec *__restrict__ hot,
+                                                   ColdRec *__restrict__ cold) {
+    const ColdRec kc = cold[slot];
+    VB_STAT(19, kc.c1 >= 0);
+    if (!(kc.c1 >= 0 && cum_eps < kc.limK)) return -1;
+    VB_STAT(14, 1);
+    QueryCtx c;
+    make_query(G.p, qx, qy, qz, c);
+    const float4 t0 = __ldg(G.hi + c0), t1 = __ldg(G.hi + kc.c1);
+    float4 t2 = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.0f), t3 = t2;
+    if (kc.c2 >= 0) t2 = __ldg(G.hi + kc.c2);
+    if (kc.c3 >= 0) t3 = __ldg(G.hi + kc.c3);
+    const float ax = c.qx - t0.x, ay = c.qy - t0.y, az = c.qz - t0.z;
+    const float bx = c.qx - t1.x, by = c.qy - t1.y, bz = c.qz - t1.z;
+    const float cx = c.qx - t2.x, cy = c.qy - t2.y, cz = c.qz - t2.z;
+    const float ex = c.qx - t3.x, ey = c.qy - t3.y, ez = c.qz - t3.z;
+    const float d0 = fmaf(az, az, fmaf(ay, ay, ax * ax));
+    const float d1 = fmaf(bz, bz, fmaf(by, by, bx * bx));
+    const float d2 = fmaf(cz, cz, fmaf(cy, cy, cx * cx));
+    const float d3 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+    const float dmin = fminf(fminf(d0, d1), fminf(d2, d3));
+    if (!(reach_now(dmin + band(G.p, dmin), cum_eps) < kc.limK)) return -1;
+    VB_STAT(15, 1);
+    // the f32-nearest member, and the nearest of the others
+    int w = 0;
+    float bw = d0;
+    if (d1 < bw) { w = 1; bw = d1; }
+    if (d2 < bw) { w = 2; bw = d2; }
+    if (d3 < bw) { w = 3; bw = d3; }
+    float rest = fminf(fminf(w == 0 ? 3.0e38f : d0, w == 1 ? 3.0e38f : d1), fminf(w == 2 ? 3.0e38f : d2, w == 3 ? 3.0e38f : d3));
+    if (!(rest - bw > band(G.p, bw) + band(G.p, rest))) {
+        w = settle_set_exact(G, qx, qy, qz, c0, kc.c1, kc.c2, kc.c3);
+        rest = fminf(fminf(w == 0 ? 3.0e38f : d0, w == 1 ? 3.0e38f : d1), fminf(w == 2 ? 3.0e38f : d2, w == 3 ? 3.0e38f : d3));
+    }
+    const int match = w == 0 ? c0 : (w == 1 ? kc.c1 : (w == 2 ? kc.c2 : kc.c3));
+    // A fresh single-candidate bound, valid as of NOW: the set's other members are at least sqrt(rest - band) away,
+    // everything outside it at least limK - cum_now.
+    const float others = fmaxf(rest - band(G.p, rest), 0.0f);
+    const float outside = __fsub_rd(kc.limK, cum_eps);
+    HotRec hn;
+    hn.c0 = match;
+    hn.lim1 = __fadd_rd(fminf(__fmul_rd(__fsqrt_rd(others), 0.999999f), outside), cum);
+    hot[slot] = hn;
+    if (w != 0) {
+        ColdRec kn = kc;
+        if (w == 1) kn.c1 = c0; else if (w == 2) kn.c2 = c0; else kn.c3 = c0;
+        cold[slot] = kn;
+    }
+    return match;
+}
+
 // ---- pass, part A: every point.  Streaming: transform, cached-neighbour tests, and for the points they settle
 // the exact decision and the estimator row.  The rest are listed per warp (ballot ranks: deterministic order)
 // for part B.  No search code in here, so the kernel runs at high occupancy: it is a gather/reduce bound by
@@ -375,6 +443,7 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
     pdl_launch_dependents();
     pdl_wait();  // the previous iteration's k_solve (T, cum) and part B (records) are complete and visible
     const ProbState *st = states + task.prob;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // the counters the NEXT pass will use: idle since the previous pass's part B finished
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         pp.work_ctr[2 * (pp.parity ^ 1)] = 0;
@@ -382,7 +451,6 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
     }
     if (st->done) return;
     __shared__ __align__(16) double rows_sh[kPassWarps][32 * kRowStride];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     PassCtx<MODE> ctx(G, st->T);
     const float cum = st->cum;
     const float cum_eps = __fadd_ru(cum, pp.pos_err);
@@ -396,73 +464,20 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
         bool hard = false;
         if (valid) {
             double vs[3];
-            ctx.transform(src_xyz + 3 * (int64_t)(task.src_begin + local), vs);
-            QueryCtx c;
-            const bool inside = make_query(G.p, vs[0], vs[1], vs[2], c);
+            ctx.transform(src_xyz, pp.src_n, task.src_begin + local, vs);
             const int slot = task.corr_begin + local;
-            if (!inside) {
+            if (!inside_grid(G.p, vs[0], vs[1], vs[2])) {
                 hot[slot].c0 = -1;  // farther than a cell outside the grid: no neighbour within the radius
             } else {
                 hard = true;
                 const HotRec h = hot[slot];
                 int match = -1;
                 if (pp.use_cache && h.c0 >= 0) {
-                    const float4 t0 = __ldg(G.hi + h.c0);
-                    const float ax = c.qx - t0.x, ay = c.qy - t0.y, az = c.qz - t0.z;
-                    const float d0 = fmaf(az, az, fmaf(ay, ay, ax * ax));
-                    // |q - c0| (upper bound) + move since the proof (upper bound) < distance to anything else then
-                    // (lower bound); a NaN or zero limit (knows nothing) compares false
-                    if (reach_now(d0 + band(G.p, d0), cum_eps) < h.lim1) {
-                        match = h.c0;
-                    } else {
-                        const ColdRec kc = cold[slot];
-                        VB_STAT(19, kc.c1 >= 0);
-                        if (kc.c1 >= 0 && cum_eps < kc.limK) {
-                            VB_STAT(14, 1);
-                            // the candidate set: is the nearest of the four nearer than anything outside can be?
-                            const float4 t1 = __ldg(G.hi + kc.c1);
-                            float4 t2 = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.0f), t3 = t2;
-                            if (kc.c2 >= 0) t2 = __ldg(G.hi + kc.c2);
-                            if (kc.c3 >= 0) t3 = __ldg(G.hi + kc.c3);
-                            const float bx = c.qx - t1.x, by = c.qy - t1.y, bz = c.qz - t1.z;
-                            const float cx = c.qx - t2.x, cy = c.qy - t2.y, cz = c.qz - t2.z;
-                            const float ex = c.qx - t3.x, ey = c.qy - t3.y, ez = c.qz - t3.z;
-                            const float d1 = fmaf(bz, bz, fmaf(by, by, bx * bx));
-                            const float d2 = fmaf(cz, cz, fmaf(cy, cy, cx * cx));
-                            const float d3 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-                            const float dmin = fminf(fminf(d0, d1), fminf(d2, d3));
-                            if (reach_now(dmin + band(G.p, dmin), cum_eps) < kc.limK) {
-                                VB_STAT(15, 1);
-                                // the f32-nearest member, and the nearest of the others
-                                int w = 0;
-                                float bw = d0;
-                                if (d1 < bw) { w = 1; bw = d1; }
-                                if (d2 < bw) { w = 2; bw = d2; }
-                                if (d3 < bw) { w = 3; bw = d3; }
-                                float rest = fminf(fminf(w == 0 ? 3.0e38f : d0, w == 1 ? 3.0e38f : d1),
-                                                   fminf(w == 2 ? 3.0e38f : d2, w == 3 ? 3.0e38f : d3));
-                                if (!(rest - bw > band(G.p, bw) + band(G.p, rest))) {
-                                    w = settle_set_exact(G, vs[0], vs[1], vs[2], h.c0, kc.c1, kc.c2, kc.c3);
-                                    rest = fminf(fminf(w == 0 ? 3.0e38f : d0, w == 1 ? 3.0e38f : d1),
-                                                 fminf(w == 2 ? 3.0e38f : d2, w == 3 ? 3.0e38f : d3));
-                                }
-                                match = w == 0 ? h.c0 : (w == 1 ? kc.c1 : (w == 2 ? kc.c2 : kc.c3));
-                                // A fresh single-candidate bound, valid as of NOW: the set's other members are at
-                                // least sqrt(rest - band) away, everything outside it at least limK - cum_now.
-                                const float others = fmaxf(rest - band(G.p, rest), 0.0f);
-                                const float outside = __fsub_rd(kc.limK, cum_eps);
-                                HotRec hn;
-                                hn.c0 = match;
-                                hn.lim1 = __fadd_rd(fminf(__fmul_rd(__fsqrt_rd(others), 0.999999f), outside), cum);
-                                hot[slot] = hn;
-                                if (w != 0) {
-                                    ColdRec kn = kc;
-                                    if (w == 1) kn.c1 = h.c0; else if (w == 2) kn.c2 = h.c0; else kn.c3 = h.c0;
-                                    cold[slot] = kn;
-                                }
-                            }
-                        }
-                    }
+                    // |q - c0| (exact, rounded up) + move since the proof (upper bound) < distance to anything else
+                    // then (lower bound); a NaN or zero limit (knows nothing) compares false
+                    const double d0x = l2_exact(vs[0], vs[1], vs[2], G.xyz + kPtStride * (int64_t)h.c0);
+                    if (reach_now(__double2float_ru(d0x), cum_eps) < h.lim1) match = h.c0;
+                    else match = settle_from_set(G, pp, vs[0], vs[1], vs[2], h.c0, slot, cum, cum_eps, hot, cold);
                 }
                 if (match >= 0) {
                     hard = false;
@@ -540,13 +555,13 @@ __device__ __forceinline__ double slot_from_gram(const double *D, bool plane, in
 // so the sums of an object do not depend on what else shares the GPU (the property sharding relies on), and
 // k_solve reads ONE row per block.  Each search refreshes the point's records.
 template <int MODE>
-__global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass_b_wl(
+__global__ void __launch_bounds__(kPassBTpb, kPassBBlocksPerSM) k_pass_b_wl(
     GridDev G, const double *__restrict__ src_xyz, const BlockTask *__restrict__ tasks,
     const ProbState *__restrict__ states, double *partials, HotRec *__restrict__ hot, ColdRec *__restrict__ cold,
     const unsigned char *__restrict__ hard_ids, const int *__restrict__ hard_cnt, PassParams pp) {
     const int lane = threadIdx.x & 31;
-    __shared__ WarpScratch wss[kPassWarps];
-    WarpScratch &ws = wss[threadIdx.x >> 5];
+    extern __shared__ __align__(16) unsigned char pass_b_smem[];  // kPassBWarps x WarpScratch
+    WarpScratch &ws = reinterpret_cast<WarpScratch *>(pass_b_smem)[threadIdx.x >> 5];
     pdl_launch_dependents();
     pdl_wait();  // part A has finished: the worklist and its length are final
     int *ctr = pp.work_ctr + 2 * pp.parity;
@@ -591,7 +606,7 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_MINBLOCKS) k_pass_b_wl(
                 const int id = hard_ids[((int64_t)blk * kPassWarps + w) * (32 * kPtsPerThread) + (h - base)];
                 const int local = (w * kPtsPerThread + (id >> 5)) * 32 + (id & 31);
                 slot = task.corr_begin + local;
-                ctx.transform(src_xyz + 3 * (int64_t)(task.src_begin + local), vs);
+                ctx.transform(src_xyz, pp.src_n, task.src_begin + local, vs);
                 make_query(G.p, vs[0], vs[1], vs[2], c);  // inside the grid, or it would not be listed
                 prior = hot[slot].c0;  // last iteration's match: a bound for this search
             }
@@ -942,9 +957,11 @@ __global__ void __launch_bounds__(256) k_src_gather(const double *__restrict__ i
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     int i = sidx[s] & ((1 << kSubShift) - 1);
-    out[3 * (int64_t)s] = in[3 * (int64_t)i];
-    out[3 * (int64_t)s + 1] = in[3 * (int64_t)i + 1];
-    out[3 * (int64_t)s + 2] = in[3 * (int64_t)i + 2];
+    // structure of arrays (x[n], y[n], z[n]): a warp's 32 consecutive points are three 256-byte requests
+    // (8 sectors each) instead of three strided ones of 24 sectors
+    out[s] = in[3 * (int64_t)i];
+    out[(int64_t)n + s] = in[3 * (int64_t)i + 1];
+    out[2 * (int64_t)n + s] = in[3 * (int64_t)i + 2];
     orig[s] = i - cloud_off[find_cloud(cloud_off, ncloud, i)];
 }
 
@@ -1130,7 +1147,7 @@ struct Batch {
     // two streams (vb200_icp_run's halves): a dependent grid that is resident early and waiting holds the registers
     // the OTHER stream's kernels need (measured: 4.6 vs 4.1 ms per converging 32-object call)
     bool chain = true;
-    double *d_src = nullptr;        // sorted source points, 3*npts
+    double *d_src = nullptr;        // sorted source points as x[npts], y[npts], z[npts]
     int *d_src_orig = nullptr;      // sorted position -> original index local to its cloud
     int *d_cloud_off = nullptr;
     // problems
@@ -1338,11 +1355,12 @@ static int batch_set_problems(Batch *b, const int32_t *cloud_ids, const double *
 // A kernel launch chained to the previous one on the stream by programmatic dependent launch (the kernels call
 // pdl_wait() before touching anything the previous kernel wrote), optionally as clusters of `cluster` blocks.
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_chained(void (*kernel)(KArgs...), int grid, int block, int cluster, cudaStream_t st,
-                                  bool chain, Args... args) {
+static cudaError_t launch_chained(void (*kernel)(KArgs...), int grid, int block, int cluster, size_t smem,
+                                  cudaStream_t st, bool chain, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
     cfg.blockDim = dim3((unsigned)block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[2];
     int na = 0;
@@ -1373,21 +1391,34 @@ static int launch_pass(Batch *b, bool plane, const PassParams &pp_in) {
     pp.parity = b->pass_parity;
     pp.brows = b->d_brows;
     pp.blk_done = b->d_blk_done;
+    pp.src_n = b->npts;
     b->pass_parity ^= 1;
-    const int nwarps = std::min(b->nblk * kBatchesPerBlock, kNumSMsB200 * kPassWarps * VB_PASS_MINBLOCKS);
-    const int nb_b = div_up(nwarps, kPassWarps);
+    // part B's scratch is dynamic shared memory (more than 48 KB per block when the block is large): opt in once
+    // per device and kernel
+    constexpr size_t kPassBSmem = sizeof(WarpScratch) * kPassBWarps;
+    if (kPassBSmem > 48 * 1024) {
+        static bool opted[64][2] = {};
+        const int dev = sc->device;
+        if (dev >= 64 || !opted[dev][plane ? 1 : 0]) {
+            if (plane) VB_CUDA(cudaFuncSetAttribute(k_pass_b_wl<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassBSmem));
+            else VB_CUDA(cudaFuncSetAttribute(k_pass_b_wl<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassBSmem));
+            if (dev < 64) opted[dev][plane ? 1 : 0] = true;
+        }
+    }
+    const int nwarps = std::min(b->nblk * kBatchesPerBlock, kNumSMsB200 * kPassBWarps * kPassBBlocksPerSM);
+    const int nb_b = div_up(nwarps, kPassBWarps);
     if (plane) {
-        VB_CUDA(launch_chained(k_pass_a<1>, b->nblk, kPassTpb, 1, st, b->chain, sc->grid, (const double *)b->d_src,
+        VB_CUDA(launch_chained(k_pass_a<1>, b->nblk, kPassTpb, 1, 0, st, b->chain, sc->grid, (const double *)b->d_src,
                                (const BlockTask *)b->d_tasks, (const ProbState *)b->d_states, b->d_partials, b->d_hot,
                                b->d_cold, b->d_hard_ids, b->d_hard_cnt, pp));
-        VB_CUDA(launch_chained(k_pass_b_wl<1>, nb_b, kPassTpb, 1, st, b->chain, sc->grid, (const double *)b->d_src,
+        VB_CUDA(launch_chained(k_pass_b_wl<1>, nb_b, kPassBTpb, 1, kPassBSmem, st, b->chain, sc->grid, (const double *)b->d_src,
                                (const BlockTask *)b->d_tasks, (const ProbState *)b->d_states, b->d_partials, b->d_hot,
                                b->d_cold, (const unsigned char *)b->d_hard_ids, (const int *)b->d_hard_cnt, pp));
     } else {
-        VB_CUDA(launch_chained(k_pass_a<0>, b->nblk, kPassTpb, 1, st, b->chain, sc->grid, (const double *)b->d_src,
+        VB_CUDA(launch_chained(k_pass_a<0>, b->nblk, kPassTpb, 1, 0, st, b->chain, sc->grid, (const double *)b->d_src,
                                (const BlockTask *)b->d_tasks, (const ProbState *)b->d_states, b->d_partials, b->d_hot,
                                b->d_cold, b->d_hard_ids, b->d_hard_cnt, pp));
-        VB_CUDA(launch_chained(k_pass_b_wl<0>, nb_b, kPassTpb, 1, st, b->chain, sc->grid, (const double *)b->d_src,
+        VB_CUDA(launch_chained(k_pass_b_wl<0>, nb_b, kPassBTpb, 1, kPassBSmem, st, b->chain, sc->grid, (const double *)b->d_src,
                                (const BlockTask *)b->d_tasks, (const ProbState *)b->d_states, b->d_partials, b->d_hot,
                                b->d_cold, (const unsigned char *)b->d_hard_ids, (const int *)b->d_hard_cnt, pp));
     }
@@ -1396,7 +1427,7 @@ static int launch_pass(Batch *b, bool plane, const PassParams &pp_in) {
 }
 
 static int launch_solve(Batch *b, const SolveParams &sp, int pass_index) {
-    VB_CUDA(launch_chained(k_solve, b->P * kSolveCtas, 256, kSolveCtas, b->stream, b->chain, (const ProbDesc *)b->d_probs,
+    VB_CUDA(launch_chained(k_solve, b->P * kSolveCtas, 256, kSolveCtas, 0, b->stream, b->chain, (const ProbDesc *)b->d_probs,
                            b->d_states, (const double *)b->d_partials, sp, pass_index));
     b->launches++;
     return VB200_OK;
@@ -1468,7 +1499,7 @@ static int batch_pass(Batch *b, int estimator, double max_dist) {
     }
     double *totals = b->d_totals_ext ? b->d_totals_ext : b->d_totals;
     if (b->nblk) VB_TRY(launch_pass(b, estimator != VB200_EST_P2P, pp));
-    VB_CUDA(launch_chained(k_reduce, b->P * kSolveCtas, 256, kSolveCtas, st, b->chain, (const ProbDesc *)b->d_probs,
+    VB_CUDA(launch_chained(k_reduce, b->P * kSolveCtas, 256, kSolveCtas, 0, st, b->chain, (const ProbDesc *)b->d_probs,
                            (const ProbState *)b->d_states, (const double *)b->d_partials,
                            estimator != VB200_EST_P2P, totals));
     b->launches++;

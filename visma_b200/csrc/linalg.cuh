@@ -38,47 +38,16 @@ __device__ __forceinline__ void cswap(bool c, double &a, double &b) {
     b = c ? t : b;
 }
 
-// determinant of an n x n matrix (n <= 6) by Gaussian elimination with partial pivoting
+// x = A^-1 b for symmetric A by LDL^T with diagonal pivoting (what Eigen's A.ldlt().solve(b) computes), and
+// det A = the product of D (a symmetric exchange of rows and columns leaves the determinant's sign alone): the
+// reference's guard |det| < 1e-6 (Utility/Eigen.cpp:41-52) needs no second factorization.  One reciprocal per
+// pivot (6 divisions in all: a division is ~30 dependent instructions, and this runs on ONE thread between two
+// correspondence passes); a zero pivot means singular: det = 0, and its column is left alone.
 template <int N>
-__device__ __forceinline__ double det_lu(const double *A) {
-    double M[N * N];
-#pragma unroll
-    for (int i = 0; i < N * N; i++) M[i] = A[i];
-    double det = 1.0;
-    bool singular = false;
-#pragma unroll
-    for (int c = 0; c < N; c++) {
-        int p = c;
-        double best = fabs(M[N * c + c]);
-#pragma unroll
-        for (int r = c + 1; r < N; r++) {
-            const double v = fabs(M[N * r + c]);
-            if (v > best) { best = v; p = r; }
-        }
-#pragma unroll
-        for (int r = c + 1; r < N; r++) {
-#pragma unroll
-            for (int k = 0; k < N; k++) cswap(p == r, M[N * c + k], M[N * r + k]);
-        }
-        if (p != c) det = -det;
-        const double piv = M[N * c + c];
-        if (piv == 0.0) singular = true;
-        det *= piv;
-#pragma unroll
-        for (int r = c + 1; r < N; r++) {
-            const double f = M[N * r + c] / piv;
-#pragma unroll
-            for (int k = c; k < N; k++) M[N * r + k] -= f * M[N * c + k];
-        }
-    }
-    return singular ? 0.0 : det;
-}
-
-// x = A^-1 b for symmetric A by LDL^T with diagonal pivoting (what Eigen's A.ldlt().solve(b) computes)
-template <int N>
-__device__ __forceinline__ void ldlt_solve(const double *A, const double *b, double *x) {
-    double M[N * N], y[N];
+__device__ __forceinline__ double ldlt_solve(const double *A, const double *b, double *x) {
+    double M[N * N], y[N], inv[N];
     int piv[N];
+    double det = 1.0;
 #pragma unroll
     for (int i = 0; i < N * N; i++) M[i] = A[i];
 #pragma unroll
@@ -93,25 +62,29 @@ __device__ __forceinline__ void ldlt_solve(const double *A, const double *b, dou
             if (v > best) { best = v; p = i; }
         }
         piv[k] = p;
-        // symmetric exchange of rows and columns k <-> p, and of the right-hand side
+        // symmetric exchange of rows and columns k <-> p, and of the right-hand side (only the trailing block and
+        // the finished columns of L in rows k, p are live)
 #pragma unroll
         for (int i = k + 1; i < N; i++) {
             const bool sw = p == i;
 #pragma unroll
             for (int c = 0; c < N; c++) cswap(sw, M[N * k + c], M[N * i + c]);
 #pragma unroll
-            for (int r = 0; r < N; r++) cswap(sw, M[N * r + k], M[N * r + i]);
+            for (int r = k; r < N; r++) cswap(sw, M[N * r + k], M[N * r + i]);
             cswap(sw, y[k], y[i]);
         }
         const double d = M[N * k + k];
+        det *= d;
+        inv[k] = d != 0.0 ? 1.0 / d : 0.0;
         if (d != 0.0) {
+            double l[N];
 #pragma unroll
-            for (int i = k + 1; i < N; i++) M[N * i + k] /= d;
+            for (int i = k + 1; i < N; i++) { l[i] = M[N * i + k]; M[N * i + k] = l[i] * inv[k]; }
 #pragma unroll
             for (int i = k + 1; i < N; i++) {
 #pragma unroll
                 for (int j = k + 1; j <= i; j++) {
-                    M[N * i + j] -= M[N * i + k] * d * M[N * j + k];
+                    M[N * i + j] -= M[N * i + k] * l[j];
                     M[N * j + i] = M[N * i + j];
                 }
             }
@@ -123,7 +96,7 @@ __device__ __forceinline__ void ldlt_solve(const double *A, const double *b, dou
         for (int j = 0; j < i; j++) y[i] -= M[N * i + j] * y[j];
     }
 #pragma unroll
-    for (int i = 0; i < N; i++) y[i] = (M[N * i + i] != 0.0) ? y[i] / M[N * i + i] : 0.0;
+    for (int i = 0; i < N; i++) y[i] *= inv[i];
 #pragma unroll
     for (int i = N - 1; i >= 0; i--) {
 #pragma unroll
@@ -137,17 +110,16 @@ __device__ __forceinline__ void ldlt_solve(const double *A, const double *b, dou
     }
 #pragma unroll
     for (int i = 0; i < N; i++) x[i] = y[i];
+    return det;
 }
 
 // SolveLinearSystem(JTJ, -JTr): false when |det| < 1e-6 or non-finite (Utility/Eigen.cpp:41-52)
 template <int N>
 __device__ inline bool solve_normal_equations(const double *JTJ, const double *JTr, double *x) {
-    double det = det_lu<N>(JTJ);
-    if (fabs(det) < 1e-6 || isnan(det) || isinf(det)) return false;
     double nb[N];
     for (int i = 0; i < N; i++) nb[i] = -JTr[i];
-    ldlt_solve<N>(JTJ, nb, x);
-    return true;
+    const double det = ldlt_solve<N>(JTJ, nb, x);
+    return !(fabs(det) < 1e-6 || isnan(det) || isinf(det));
 }
 
 // R = Rz(x2) Ry(x1) Rx(x0), t = x3..5 (Utility/Eigen.cpp:58-68)

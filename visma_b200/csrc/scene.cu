@@ -112,13 +112,16 @@ __global__ void __launch_bounds__(kTpb) k_gather(GridParams g, const unsigned lo
     if (s >= n) return;
     int i = (int)(unsigned int)skey[s];
     double x = xyz_in[3 * (int64_t)i], y = xyz_in[3 * (int64_t)i + 1], z = xyz_in[3 * (int64_t)i + 2];
-    xyz[kPtStride * s] = x; xyz[kPtStride * s + 1] = y; xyz[kPtStride * s + 2] = z;
+    // 32-byte records, written as two 16-byte stores
+    double2 *xr = reinterpret_cast<double2 *>(xyz + kPtStride * s);
+    xr[0] = make_double2(x, y);
+    xr[1] = make_double2(z, 0.0);
     hi[s] = make_float4((float)(x - g.ctr[0]), (float)(y - g.ctr[1]), (float)(z - g.ctr[2]), __int_as_float(i));
     orig[s] = i;
     if (nrm_in) {
-        nrm[kPtStride * s] = nrm_in[3 * (int64_t)i];
-        nrm[kPtStride * s + 1] = nrm_in[3 * (int64_t)i + 1];
-        nrm[kPtStride * s + 2] = nrm_in[3 * (int64_t)i + 2];
+        double2 *nr = reinterpret_cast<double2 *>(nrm + kPtStride * s);
+        nr[0] = make_double2(nrm_in[3 * (int64_t)i], nrm_in[3 * (int64_t)i + 1]);
+        nr[1] = make_double2(nrm_in[3 * (int64_t)i + 2], 0.0);
     }
 }
 
@@ -226,7 +229,7 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     VB_CUDA(d_hi.alloc((size_t)n));
     VB_CUDA(d_xyz.alloc(kPtStride * (size_t)n));
     VB_CUDA(d_orig.alloc((size_t)n));
-    if (h_nrm) VB_CUDA(d_nrm.alloc(3 * (size_t)n));
+    if (h_nrm) VB_CUDA(d_nrm.alloc(kPtStride * (size_t)n));
     double *const nrm_out = d_nrm.p;
     k_fine_starts<<<div_up(ncoarse, 128), 128, 0, st>>>((int)ncoarse, d_cstart.p, d_skey.p, d_cmask.p,
                                                          d_cbase.p, d_coarse.p, d_fstart.p, nfine, (int)n);
