@@ -272,7 +272,11 @@ def knn_sweep_leg(dev, flush, peak):
                "bruteforce_GBps": (16 * N + 24 * Q) / (bf_ms * 1e-3) / 1e9,
                "bruteforce_frac_of_peak": (16 * N + 24 * Q) / (bf_ms * 1e-3) / 1e9 / peak,
                "grid_equals_bruteforce_bit_for_bit": same, "matched": int((idx >= 0).sum().item()),
-               "scene_create_s_incl_h2d": build_s}
+               "scene_create_s_incl_h2d": build_s,
+               # N x Q pairs, 3 FFMA each (f32-screened kernel): the brute-force leg is bound by the FP32 pipe at this
+               # Q, so its roofline is 128 FFMA lanes x 148 SMs x the SM clock, not HBM
+               "bruteforce_pairs_per_s": N * Q / (bf_ms * 1e-3),
+               "bruteforce_fp32_frac_of_peak": 3.0 * N * Q / (bf_ms * 1e-3) / (128 * 148 * 1.965e9)}
         # CPU side on a bounded size: the reference's KD-tree (FLANN) build + the same 10 000 queries, and parity
         if N <= 1_000_000:
             try:
@@ -297,7 +301,10 @@ def knn_sweep_leg(dev, flush, peak):
     return {"peak_GBps": peak, "rows": rows,
             "note": "GB/s = SURVEY §8d algorithmic bytes (16N + 24Q: the scene once) / launch time.  The grid search "
                     "reads only the cells near the queries (ncu dram bytes: profiles/), so for it the fraction "
-                    "describes the metric, not DRAM utilisation; the brute-force kernel really streams the scene."}
+                    "describes the metric, not DRAM utilisation.  The brute-force kernel does N x Q distance evaluations "
+                    "(1e11 at N = 1e7): FP32-bound, f32 screen (3 FFMA + compare per pair over TMA-staged float4 "
+                    "tiles) with exact f64 re-evaluation of the pairs inside the error band; "
+                    "bruteforce_fp32_frac_of_peak = 3 N Q / t / (128 lanes x 148 SMs x 1.965 GHz)."}
 
 
 def render_leg(dev, peak):

@@ -64,6 +64,9 @@ def test_near_ties_resolved_in_double(vb, oracle):
     gi, gd = sc.SearchHybrid1(base, 0.075)
     oi, od = oracle.Index(tgt, 0.075).knn1(base, 0.075)
     assert (gi == oi).all() and (gd == od).all()
+    # the exhaustive search screens in f32 too (from 16 queries up): same answers, and with the screen switched off
+    bi, bd = vb.reg.SearchHybrid1BruteForce(tgt, base, 0.075)
+    assert (bi == oi).all() and (bd == od).all()
 
 
 def test_docs_kat_correspondences(vb, oracle, kat):
@@ -142,6 +145,20 @@ def test_bruteforce_matches_oracle_bitexact(vb, oracle):
     q = np.array([[1.01, 0, 0], [1.0, 0, 0], [0, 0, 0.0], [3, 3, 3.0]])
     gi, gd = vb.reg.SearchHybrid1BruteForce(tgt, q, 0.075)
     assert list(gi) == [2, 2, 0, -1] and gd[3] == 0.0
+    # the same through the f32-screened kernel (16 queries or more), with the acceptance threshold's edge cases
+    r2f = float(np.float32(0.075 * 0.075))
+    d_in, d_out = np.sqrt(min(r2f, 0.075 * 0.075)) * (1 - 1e-9), np.sqrt(max(r2f, 0.075 * 0.075)) * (1 + 1e-9)
+    q16 = np.concatenate([q, [[d_in, 0, 0], [np.sqrt((r2f + 0.075 * 0.075) / 2), 0, 0], [d_out, 0, 0]], np.tile(q, (4, 1))])
+    gi, gd = vb.reg.SearchHybrid1BruteForce(tgt, q16, 0.075)
+    oi, od = oracle.Index(tgt, 0.075).knn1(q16, 0.075)
+    assert (gi == oi).all() and (gd == od).all() and list(gi[:4]) == [2, 2, 0, -1] and gi[4] == 0 and gi[6] == -1
+    # far from the origin: the screen centres the coordinates (a cloud 1 km away keeps millimetre structure in f32)
+    far = np.array([1000.0, -2000.0, 500.0])
+    tg2 = rng.uniform(0, 1, (6000, 3)) + far
+    q2 = tg2[:400] + rng.normal(0, 0.003, (400, 3))
+    gi, gd = vb.reg.SearchHybrid1BruteForce(tg2, q2, 0.075)
+    oi, od = oracle.Index(tg2, 0.075).knn1(q2, 0.075)
+    assert (gi == oi).all() and (gd == od).all()
     gi, gd = vb.reg.SearchHybrid1BruteForce(np.zeros((0, 3)), q, 0.075)
     assert (gi == -1).all() and (gd == 0).all()
     gi, gd = vb.reg.SearchHybrid1BruteForce(tgt, np.zeros((0, 3)), 0.075)
