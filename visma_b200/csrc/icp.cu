@@ -47,8 +47,8 @@ constexpr int kPassWarps = kPassTpb / 32;  // every warp writes its own partial:
 #ifndef VB_PASS_PTS
 #define VB_PASS_PTS 4
 #endif
-constexpr int kPtsPerThread = VB_PASS_PTS;
-constexpr int kChunk = kPassTpb * kPtsPerThread;  // source points per block
+constexpr int kPtsPerThread = VB_PASS_PTS;  // the most a part-A thread takes (Batch::pts picks 4, 2 or 1 per batch of problems)
+constexpr int kChunk = kPassTpb * kPtsPerThread;  // the most source points a block covers
 constexpr int kAcc = 32;                          // accumulator slots (padded)
 constexpr int kBuckets = 32768;                   // spatial buckets per source cloud (15-bit key)
 
@@ -117,6 +117,7 @@ struct PassParams {
     double *brows;    // per (block, batch): the batch's Gram matrix, until the block's last batch folds them
     int *blk_done;    // per block: batches finished in this pass (reset by the one that folds)
     int64_t src_n;    // points in the batch's source array (x[src_n], y[src_n], z[src_n])
+    int pts;          // points per part-A thread: a block covers kPassTpb * pts consecutive points (see Batch::pts)
 };
 
 #ifndef VB_SLACK_LO_PCT
@@ -454,11 +455,11 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
     PassCtx<MODE> ctx(G, st->T);
     const float cum = st->cum;
     const float cum_eps = __fadd_ru(cum, pp.pos_err);
-    unsigned char *my_hard = hard_ids + ((int64_t)blockIdx.x * kPassWarps + warp) * (32 * kPtsPerThread);
+    unsigned char *my_hard = hard_ids + ((int64_t)blockIdx.x * kPassWarps + warp) * (32 * pp.pts);
     int nhard = 0;  // warp-uniform
 #pragma unroll 1
-    for (int k = 0; k < kPtsPerThread; k++) {
-        const int local = (warp * kPtsPerThread + k) * 32 + lane;
+    for (int k = 0; k < pp.pts; k++) {
+        const int local = (warp * pp.pts + k) * 32 + lane;
         const bool valid = local < task.count;
         double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         bool hard = false;
@@ -566,6 +567,7 @@ __global__ void __launch_bounds__(kPassBTpb, kPassBBlocksPerSM) k_pass_b_wl(
     pdl_wait();  // part A has finished: the worklist and its length are final
     int *ctr = pp.work_ctr + 2 * pp.parity;
     const int n_items = ctr[0];
+    if (n_items == 0) return;  // nothing was listed: not even the hand-out counter is touched
 #pragma unroll 1
     for (;;) {
         int item = 0;
@@ -603,8 +605,8 @@ __global__ void __launch_bounds__(kPassBTpb, kPassBBlocksPerSM) k_pass_b_wl(
 #pragma unroll
                 for (int i = 0; i < kPassWarps - 1; i++)
                     if (h >= seg_end[i]) { w = i + 1; base = seg_end[i]; }
-                const int id = hard_ids[((int64_t)blk * kPassWarps + w) * (32 * kPtsPerThread) + (h - base)];
-                const int local = (w * kPtsPerThread + (id >> 5)) * 32 + (id & 31);
+                const int id = hard_ids[((int64_t)blk * kPassWarps + w) * (32 * pp.pts) + (h - base)];
+                const int local = (w * pp.pts + (id >> 5)) * 32 + (id & 31);
                 slot = task.corr_begin + local;
                 ctx.transform(src_xyz, pp.src_n, task.src_begin + local, vs);
                 make_query(G.p, vs[0], vs[1], vs[2], c);  // inside the grid, or it would not be listed
@@ -628,7 +630,18 @@ __global__ void __launch_bounds__(kPassBTpb, kPassBBlocksPerSM) k_pass_b_wl(
         }
         // the batch's row; then, if this was the block's last batch to finish, fold the block's rows in batch order
         const int nb = (total + 31) >> 5;
-        double2 *brow = reinterpret_cast<double2 *>(pp.brows + ((int64_t)blk * kBatchesPerBlock) * kPart);
+        if (nb == 1) {
+            // the block's only batch (every listed block of a settled pass): row = part A's + batch 0, as below, without
+            // the trip through the batch rows and the block's counter
+            double2 *arow = reinterpret_cast<double2 *>(partials + (int64_t)blk * kPart);
+            const double2 mine = ctx.lane_pair();
+            double2 t = arow[lane];
+            t.x += mine.x; t.y += mine.y;
+            arow[lane] = t;
+            __syncwarp();
+            continue;
+        }
+        double2 *brow = reinterpret_cast<double2 *>(pp.brows + ((int64_t)blk * (kPassWarps * pp.pts)) * kPart);
         brow[k * (kPart / 2) + lane] = ctx.lane_pair();
         __threadfence();
         int prev = 0;
@@ -731,6 +744,11 @@ __device__ double update_move_bound(const double *U, const double *T, const doub
 // from the reduced slots; one thread.  npts = source points the totals were accumulated over.
 __device__ void solve_from_totals(const double *tot, double npts, const ProbDesc &pd, ProbState *st,
                                   const SolveParams &sp, int pass_index) {
+    // everything read from the state before anything is written to it
+    const double prev_fitness = st->prev_fitness, prev_rmse = st->prev_rmse;
+    const float cum = st->cum;
+    double U[16], T[16];
+    for (int i = 0; i < 16; i++) T[i] = st->T[i];
     const double K = tot[kSlotCount];
     double fitness = 0.0, rmse = 0.0;
     if (K > 0.0 && npts > 0.0) {
@@ -740,8 +758,7 @@ __device__ void solve_from_totals(const double *tot, double npts, const ProbDesc
     st->fitness = fitness;
     st->rmse = rmse;
     st->ncorr = (int)K;
-    if (pass_index >= 1 && fabs(st->prev_fitness - fitness) < sp.rel_fitness &&
-        fabs(st->prev_rmse - rmse) < sp.rel_rmse) {
+    if (pass_index >= 1 && fabs(prev_fitness - fitness) < sp.rel_fitness && fabs(prev_rmse - rmse) < sp.rel_rmse) {
         st->done = 1;
         if (sp.ndone) atomicAdd(sp.ndone, 1);
         return;
@@ -753,8 +770,6 @@ __device__ void solve_from_totals(const double *tot, double npts, const ProbDesc
         if (sp.ndone) atomicAdd(sp.ndone, 1);
         return;
     }
-    double U[16], T[16];
-    for (int i = 0; i < 16; i++) T[i] = st->T[i];
     if (sp.estimator == VB200_EST_P2P) {
         const double cref[3] = {T[3], T[7], T[11]};
         update_p2p(tot, cref, U);
@@ -762,9 +777,9 @@ __device__ void solve_from_totals(const double *tot, double npts, const ProbDesc
         update_p2plane(tot, sp, U);
     }
     const float moved = __double2float_ru(update_move_bound(U, T, pd.ctr, pd.rad));
-    st->last_move = moved;
-    st->cum = __fadd_ru(st->cum, moved);
     mat4_mul(U, T, T);
+    st->last_move = moved;
+    st->cum = __fadd_ru(cum, moved);
     for (int i = 0; i < 16; i++) st->T[i] = T[i];
     st->iters = pass_index + 1;
 }
@@ -1169,6 +1184,12 @@ struct Batch {
     double *d_brows = nullptr;               // per (block, batch): the batch's Gram row until the block's rows are folded
     int *d_blk_done = nullptr;               // per block: batches finished in the current pass
     int pass_parity = 0;
+    // Points per part-A thread (4, 2 or 1; a block covers 128 x pts points).  A warp walks its pts batches one after the
+    // other, three dependent round trips each: with many objects on the GPU four batches per warp keep the block count
+    // (and the per-block partial rows) down at no cost, with few — 4 objects per GPU when 32 are sharded over 8 — the
+    // blocks would not fill the machine and the walk's latency chain is the whole kernel (ncu: 20 us for 11 MB), so the
+    // points are spread over more, shorter-lived blocks.
+    int pts = kPtsPerThread;
     int64_t launches = 0;
     int iter_base = 0;                       // running pass index for vb200_batch_iterate
     double *d_totals = nullptr;              // P x kAcc, library-owned unless the caller supplied a buffer
@@ -1282,6 +1303,18 @@ static int batch_set_problems_impl(Batch *b, const int32_t *cloud_ids, const dou
     }
     batch_free_problems(b);  // P = 0 from here until every upload below has succeeded
     b->iter_base = 0;
+    // points per part-A thread: the largest of 4, 2, 1 that still gives part A one full wave of blocks
+    b->pts = kPtsPerThread;
+    for (;;) {
+        int64_t nb = 0;
+        for (int p = 0; p < P; p++) {
+            const int c = cloud_ids ? cloud_ids[p] : p;
+            nb += div_up(b->cloud_off[c + 1] - b->cloud_off[c], kPassTpb * b->pts);
+        }
+        if (b->pts == 1 || nb >= (int64_t)kNumSMsB200 * VB_PASS_A_MINBLOCKS) break;
+        b->pts >>= 1;
+    }
+    const int chunk = kPassTpb * b->pts, batches_per_block = kPassWarps * b->pts;
     b->probs.resize((size_t)P);
     std::vector<BlockTask> tasks;
     std::vector<ProbState> states((size_t)P);
@@ -1296,11 +1329,11 @@ static int batch_set_problems_impl(Batch *b, const int32_t *cloud_ids, const dou
         pd.blk_begin = (int)tasks.size();
         for (int a = 0; a < 3; a++) pd.ctr[a] = b->cloud_sphere[4 * (size_t)c + a];
         pd.rad = b->cloud_sphere[4 * (size_t)c + 3];
-        for (int s = 0; s < pd.npts; s += kChunk) {
+        for (int s = 0; s < pd.npts; s += chunk) {
             BlockTask t;
             t.prob = p;
             t.src_begin = pd.src_begin + s;
-            t.count = std::min(kChunk, pd.npts - s);
+            t.count = std::min(chunk, pd.npts - s);
             t.corr_begin = pd.corr_begin + s;
             tasks.push_back(t);
         }
@@ -1318,7 +1351,7 @@ static int batch_set_problems_impl(Batch *b, const int32_t *cloud_ids, const dou
     VB_CUDA(cudaMallocAsync((void **)&b->d_states, sizeof(ProbState) * P1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_tasks, sizeof(BlockTask) * nblk1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_partials, sizeof(double) * kPart * nblk1, st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_brows, sizeof(double) * kPart * kBatchesPerBlock * nblk1, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_brows, sizeof(double) * kPart * (size_t)batches_per_block * nblk1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_blk_done, sizeof(int) * nblk1, st));
     VB_CUDA(cudaMemsetAsync(b->d_blk_done, 0, sizeof(int) * nblk1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_hot, sizeof(HotRec) * nslot, st));
@@ -1332,11 +1365,11 @@ static int batch_set_problems_impl(Batch *b, const int32_t *cloud_ids, const dou
     // 0xff: c = -1 (no match, no candidates), limits NaN (every test compares false): knows nothing
     VB_CUDA(cudaMemsetAsync(b->d_hot, 0xff, sizeof(HotRec) * nslot, st));
     VB_CUDA(cudaMemsetAsync(b->d_cold, 0xff, sizeof(ColdRec) * nslot, st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_hard_ids, (size_t)kChunk * nblk1, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_hard_ids, (size_t)chunk * nblk1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_hard_cnt, sizeof(int) * kPassWarps * nblk1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_ndone, sizeof(int), st));
     VB_CUDA(cudaMemsetAsync(b->d_ndone, 0, sizeof(int), st));
-    VB_CUDA(cudaMallocAsync((void **)&b->d_work, sizeof(int) * kBatchesPerBlock * nblk1, st));
+    VB_CUDA(cudaMallocAsync((void **)&b->d_work, sizeof(int) * (size_t)batches_per_block * nblk1, st));
     VB_CUDA(cudaMallocAsync((void **)&b->d_work_ctr, sizeof(int) * 4, st));
     VB_CUDA(cudaMemsetAsync(b->d_work_ctr, 0, sizeof(int) * 4, st));
     b->pass_parity = 0;
@@ -1392,6 +1425,7 @@ static int launch_pass(Batch *b, bool plane, const PassParams &pp_in) {
     pp.brows = b->d_brows;
     pp.blk_done = b->d_blk_done;
     pp.src_n = b->npts;
+    pp.pts = b->pts;
     b->pass_parity ^= 1;
     // part B's scratch is dynamic shared memory (more than 48 KB per block when the block is large): opt in once
     // per device and kernel
@@ -1405,7 +1439,7 @@ static int launch_pass(Batch *b, bool plane, const PassParams &pp_in) {
             if (dev < 64) opted[dev][plane ? 1 : 0] = true;
         }
     }
-    const int nwarps = std::min(b->nblk * kBatchesPerBlock, kNumSMsB200 * kPassBWarps * kPassBBlocksPerSM);
+    const int nwarps = (int)std::min<int64_t>((int64_t)b->nblk * kPassWarps * b->pts, kNumSMsB200 * kPassBWarps * kPassBBlocksPerSM);
     const int nb_b = div_up(nwarps, kPassBWarps);
     if (plane) {
         VB_CUDA(launch_chained(k_pass_a<1>, b->nblk, kPassTpb, 1, 0, st, b->chain, sc->grid, (const double *)b->d_src,
