@@ -661,6 +661,19 @@ __device__ __forceinline__ Top5 top5_of_near(const GridDev &G, const QueryCtx &c
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// one listed run: its start / length and the drop threshold h (see list_runs)
+template <int TPB>
+__device__ __forceinline__ void store_run(const GridParams &g, LaneRuns<TPB> &L, int n, int tid, int s0, int s1, float gap2,
+                                          float slack) {
+    // (h only has to err low: the square root comes from the 2-ulp reciprocal-square-root unit, deflated; sqrt(gp) = sg)
+    const float sg = fmaxf(gap2 * rsqrtf(fmaxf(gap2, 1e-30f)) * 0.99999f - slack, 0.0f) * 0.999999f;
+    const float gp = sg * sg;
+    const float bnd = fmaf(g.band_a * 1.001f, sg, fmaf(g.band_rel * 1.001f, gp, g.band_b * 1.001f));
+    const float h = fmaxf(fmaf(-2.0f, bnd, gp), 0.0f);
+    L.s0[n][tid] = s0;
+    L.w[n][tid] = (__float_as_uint(h) & ~kRunLenMask) | (unsigned)(s1 - s0);
+}
+
 // list the occupied fine cells with done < gap2 <= thr (squared distance to the query, deflated) as runs, in ONE
 // flat loop over the cells of the query's box (nested loops with per-lane trip counts serialise: measured 30 passes
 // of the inner body per warp for 2.5 runs per lane; a warp-cooperative walk over the UNION of the lanes' boxes was
@@ -706,12 +719,7 @@ __device__ __forceinline__ int list_runs(const GridDev &G, const QueryCtx &c, fl
                     z = z1; y = y1; x = x1;
                 } else {
                     prefetch_l1(G.hi + s0);
-                    const float sg = fmaxf(sqrtf(gap2) - slack, 0.0f) * 0.999999f;
-                    const float gp = sg * sg;
-                    const float bnd = fmaf(g.band_a * 1.001f, sqrtf(gp), fmaf(g.band_rel * 1.001f, gp, g.band_b * 1.001f));
-                    const float h = fmaxf(fmaf(-2.0f, bnd, gp), 0.0f);
-                    L.s0[n][tid] = s0;
-                    L.w[n][tid] = (__float_as_uint(h) & ~kRunLenMask) | (unsigned)(s1 - s0);
+                    store_run<TPB>(g, L, n, tid, s0, s1, gap2, slack);
                     ++n;
                 }
             }
@@ -723,6 +731,83 @@ __device__ __forceinline__ int list_runs(const GridDev &G, const QueryCtx &c, fl
         ox = wx ? ox0 : ox + 1.0f;
         y = wy ? y0 : (wx ? y + 1 : y);
         oy = wy ? oy0 : (wx ? oy + 1.0f : oy);
+        z += wy ? 1 : 0;
+        oz += wy ? 1.0f : 0.0f;
+        if (z > z1) break;
+    }
+    return n;
+}
+
+// The same list by ROWS of the box instead of cells, for a lane's first round (nothing scanned yet).  Inside a coarse
+// cell the fine cells are stored in the order x + 4 y + 16 z, so the cells of one box row (fixed y, z; consecutive x)
+// that share a coarse cell are ONE contiguous run of the sorted arrays: its ends are two ranks in the coarse cell's
+// occupancy mask.  A box of up to 4 x 4 x 4 cells is walked as at most 16 rows x 2 segments (a row crosses at most one
+// coarse-cell boundary) instead of up to 64 cells — the walk over the cells of a lane's box was 38 % of part B's
+// instructions at 11.7 of 32 lanes.  Each row is trimmed to the cells within reach along x (one square root); a
+// run's drop threshold comes from the distance to its nearest cell.  The listed cells are a superset of those the
+// per-cell test accepts, which is all the search's bookkeeping needs (every cell with gap2 <= thr is scanned).
+template <int TPB>
+__device__ __forceinline__ int list_rows(const GridDev &G, const QueryCtx &c, float thr, float slack, LaneRuns<TPB> &L) {
+    const GridParams &g = G.p;
+    const int tid = threadIdx.x & (TPB - 1);
+    const float fine2 = g.fine * g.fine;
+    const float rho = sqrtf(thr) / g.fine * 1.0011f + 1e-4f;  // (as list_runs: covers the deflated gap test)
+    const int x0 = max(c.gx - (int)ceilf(fmaxf(rho - c.fx, 0.0f)), 0),
+              x1 = min(c.gx + (int)ceilf(fmaxf(rho - (1.0f - c.fx), 0.0f)), g.fdim[0] - 1);
+    const int y0 = max(c.gy - (int)ceilf(fmaxf(rho - c.fy, 0.0f)), 0),
+              y1 = min(c.gy + (int)ceilf(fmaxf(rho - (1.0f - c.fy), 0.0f)), g.fdim[1] - 1);
+    const int z0 = max(c.gz - (int)ceilf(fmaxf(rho - c.fz, 0.0f)), 0),
+              z1 = min(c.gz + (int)ceilf(fmaxf(rho - (1.0f - c.fz), 0.0f)), g.fdim[2] - 1);
+    if (x1 - x0 > 3) return kLaneMaxRuns + 1;  // (never at a lane-private reach: a row would span three coarse cells)
+    // the two x segments: [x0, xm] in the first coarse cell, (xm, x1] in the next one (empty unless the row crosses)
+    const int xm = min(x1, x0 | 3);
+    const bool two = x1 > xm;
+    // the reach in cell units, inflated like the box: a cell is within reach along x iff its ex <= sqrt(rho2 - ey^2 - ez^2)
+    const float rho2 = rho * rho;
+    int n = 0;
+    int y = y0, z = z0;
+    bool second = false;
+    const float oy0 = (float)(y0 - c.gy);
+    float oy = oy0, oz = (float)(z0 - c.gz);
+    for (;;) {
+        const float ey = fmaxf(fmaxf(oy - c.fy, c.fy - oy - 1.0f), 0.0f);
+        const float ez = fmaxf(fmaxf(oz - c.fz, c.fz - oz - 1.0f), 0.0f);
+        const float eyz2 = ey * ey + ez * ez;
+        const float w2 = rho2 - eyz2;
+        if (w2 >= 0.0f) {
+            // cells of this segment within reach along x: offsets ox (from the home cell) with max(ox - fx, fx - ox - 1) <= w
+            // (sqrt by the 2-ulp reciprocal-square-root unit, inflated: only a superset is needed; conversions with the
+            // rounding built in)
+            const float w = fmaf(w2, rsqrtf(fmaxf(w2, 1e-30f)), 1e-5f) * 1.0001f;
+            const int sa = second ? xm + 1 : x0, sb = second ? x1 : xm;
+            const int xa = max(sa, c.gx + __float2int_ru(c.fx - w - 1.0f)), xb = min(sb, c.gx + __float2int_rd(c.fx + w));
+            if (xa <= xb) {
+                const CoarseCell cc = G.coarse[((z >> 2) * g.cdim[1] + (y >> 2)) * g.cdim[0] + (xa >> 2)];
+                const int b0 = (xa & 3) + 4 * (y & 3) + 16 * (z & 3), b1 = b0 + (xb - xa);
+                const unsigned long long below0 = (1ull << b0) - 1ull, upto1 = b1 == 63 ? ~0ull : ((2ull << b1) - 1ull);
+                const int r0 = __popcll(cc.mask & below0), r1 = __popcll(cc.mask & upto1);
+                if (r1 > r0) {
+                    const int s0 = __ldg(G.fstart + cc.base + r0), s1 = __ldg(G.fstart + cc.base + r1);
+                    if (n >= kLaneMaxRuns || s1 - s0 > (int)kRunLenMask) {
+                        n = kLaneMaxRuns + 1;  // fall back; end the walk
+                        z = z1; y = y1; second = two;
+                    } else {
+                        prefetch_l1(G.hi + s0);
+                        // distance to the segment's nearest cell, deflated as in list_runs
+                        const float oxa = (float)(xa - c.gx), oxb = (float)(xb - c.gx);
+                        const float ex = fmaxf(fmaxf(oxa - c.fx, c.fx - oxb - 1.0f), 0.0f);
+                        const float gap2 = fmaxf((ex * ex + eyz2) * fine2 * 0.998f - 1e-12f * fine2, 0.0f);
+                        store_run<TPB>(g, L, n, tid, s0, s1, gap2, slack);
+                        ++n;
+                    }
+                }
+            }
+        }
+        // step (segment, y, z) with selects only: one backward branch, the lanes of a warp stay converged
+        const bool ws = second || !two, wy = ws && y == y1;
+        second = ws ? false : true;
+        y = wy ? y0 : (ws ? y + 1 : y);
+        oy = wy ? oy0 : (ws ? oy + 1.0f : oy);
         z += wy ? 1 : 0;
         oz += wy ? 1.0f : 0.0f;
         if (z > z1) break;
@@ -801,7 +886,8 @@ __device__ __forceinline__ int nn_search_hybrid(const GridDev &G, bool valid, co
         if (!__any_sync(FULL, mode == kScan)) break;
         int steps = 0;
         if (mode == kScan) {
-            const int nruns = list_runs<TPB>(G, c, thr, done, slack, L);
+            // (first round: nothing scanned yet, the box is listed by rows; a second round lists the cells it adds)
+            const int nruns = done < 0.0f ? list_rows<TPB>(G, c, thr, slack, L) : list_runs<TPB>(G, c, thr, done, slack, L);
             if (nruns > kLaneMaxRuns) {
                 mode = kCoop;
                 VB_STAT(5, 1);
