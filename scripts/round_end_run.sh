@@ -6,12 +6,10 @@ tag=${1:-r1s3}
 out=gpurun_out
 mkdir -p $out
 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; tail -3 $out/${tag}_pytest_gpu.log
-VB200_KNN_WPQ=seq python -m pytest tests/test_gpu_knn.py -m gpu -x -q > $out/${tag}_pytest_knn_seq.log 2>&1; tail -1 $out/${tag}_pytest_knn_seq.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 python bench.py > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench_1gpu.err; tail -c 400 $out/${tag}_bench_1gpu.json
 python scripts/bench_render.py > $out/${tag}_render_bench.json 2> $out/${tag}_render.err; tail -c 500 $out/${tag}_render_bench.json
 python scripts/bench_knn_sweep.py > $out/${tag}_knn_sweep.json 2> $out/${tag}_knn_sweep.err
-VB200_KNN_WPQ=seq python scripts/bench_knn_sweep.py 1e5 1e6 > $out/${tag}_knn_sweep_seq.json 2>> $out/${tag}_knn_sweep.err
 python - <<PY
 import json
 for f in ("$out/${tag}_knn_sweep.json", "$out/${tag}_knn_sweep_seq.json"):

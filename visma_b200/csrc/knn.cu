@@ -573,10 +573,8 @@ int knn1_launch(Scene *sc, const double *d_q, int64_t nq, double radius, int *d_
     if (nq > 0x7fffffff) return VB200_ERR_INVALID;
     const double r2 = (double)(float)(radius * radius);  // KDTreeFlann.cpp:185
     if (nq <= kWarpPerQueryMax) {
-        // dev knob VB200_KNN_WPQ=seq: the sequential cell walk instead of the breadth-first one (same results)
-        static const int bfs = []() { const char *e = getenv("VB200_KNN_WPQ"); return !(e && e[0] == 's'); }();
         k_knn1_wpq<<<div_up(nq * 32, kTpb), kTpb, 0, sc->stream>>>(sc->grid, d_q, nq, r2,
-                                                                   r2_upper_bound(sc->grid.p, r2), bfs, d_idx, d_d2);
+                                                                   r2_upper_bound(sc->grid.p, r2), 1, d_idx, d_d2);
         VB_CUDA(cudaGetLastError());
         return VB200_OK;
     }

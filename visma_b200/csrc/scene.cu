@@ -151,9 +151,7 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     // also grown if the dense coarse array would exceed 2^27 cells.
     GridParams &g = sc->grid.p;
     double scale = 1.0;
-    const char *force = getenv("VB200_CELL_SCALE");  // dev knob: fixed scale, no adaptation
-    if (force && atof(force) >= 1.0) scale = atof(force);
-  for (int attempt = force ? 4 : 0;; attempt++) {
+  for (int attempt = 0;; attempt++) {
     double cell = max_radius * scale;
     for (;;) {
         double cells = 1.0;
@@ -213,7 +211,7 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     VB_CUDA(cudaMemcpyAsync(&nfine, d_total.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     VB_CUDA(cudaStreamSynchronize(st));
     sc->nfine = nfine;
-    static const double occ_target = getenv("VB200_OCC_TARGET") ? atof(getenv("VB200_OCC_TARGET")) : 5.0;  // dev knob
+    constexpr double occ_target = 5.0;  // points per occupied fine cell below which the cell is grown
     if ((double)n / (double)std::max(nfine, 1) < occ_target && attempt < 4 && n > 1000) {
         static const double kScales[5] = {1.0, 1.5, 2.0, 3.0, 4.0};  // measured optimum is flat between 1.5 and 2
         scale = kScales[attempt + 1];
