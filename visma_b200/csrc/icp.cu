@@ -66,7 +66,9 @@ struct ProbState {
     // bounds the move of every point between them, which is all the cached-neighbour tests need to know.
     float cum;
     float last_move;  // the latest update's share (huge before the first update)
-    int pad;
+    // the cloud's bounding sphere under the current transform lies inside the grid (k_solve's verdict, rigorous, 0 until
+    // the first update): part A then skips the per-point range test
+    int all_inside;
 };
 
 struct BlockTask {
@@ -152,6 +154,7 @@ struct SolveParams {
     int max_iter;
     int estimator;
     int *ndone;  // nullable: counts the problems that have finished (lets the host stop enqueueing iterations)
+    double box_lo[3], box_hi[3];  // the scene grid's box, shrunk by a rounding margin (for ProbState::all_inside)
 };
 
 // ---- programmatic dependent launch: the three kernels of an iteration are chained with
@@ -274,6 +277,12 @@ struct PassCtx {
                                              double (&x)[8]) {
         const double d2 = l2_exact(vs[0], vs[1], vs[2], vt[0], vt[1], vt[2]);
         if (!(d2 < r2)) return false;
+        fill_row(vs, vt, nt, d2, x);
+        return true;
+    }
+    // the accepted match's estimator row and its share of the pass's sums
+    __device__ __forceinline__ void fill_row(const double (&vs)[3], const double (&vt)[3], const double (&nt)[3], double d2,
+                                             double (&x)[8]) {
         if (MODE == 1) {
             x[0] = vs[1] * nt[2] - vs[2] * nt[1];
             x[1] = vs[2] * nt[0] - vs[0] * nt[2];
@@ -289,7 +298,6 @@ struct PassCtx {
         }
         sum_d2 += d2;
         count += 1;
-        return true;
     }
     // ... for match candidate bs (>= 0), gathered here: one 256-bit load per record
     __device__ __forceinline__ bool row_of(int bs, const double (&vs)[3], double r2, double (&x)[8]) {
@@ -301,6 +309,34 @@ struct PassCtx {
             nt[0] = nn.x; nt[1] = nn.y; nt[2] = nn.z;
         }
         return row_from(vs, vt, nt, r2, x);
+    }
+
+    // Part A's form: the lane's row goes straight into its slot of the warp's staging area (no 8-double row held in
+    // registers across the point's tests: at 40 registers it lived in local memory), zeros for a lane without a match.
+    __device__ __forceinline__ void stage_row(double *rows, const double (&vs)[3], const double (&vt)[3], const double (&nt)[3],
+                                              double d2) {
+        double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        fill_row(vs, vt, nt, d2, x);
+        double2 *row = reinterpret_cast<double2 *>(rows + (threadIdx.x & 31) * kRowStride);
+        row[0] = make_double2(x[0], x[1]);
+        row[1] = make_double2(x[2], x[3]);
+        row[2] = make_double2(x[4], x[5]);
+        row[3] = make_double2(x[6], x[7]);
+    }
+    __device__ __forceinline__ void stage_zero_row(double *rows) {
+        double2 *row = reinterpret_cast<double2 *>(rows + (threadIdx.x & 31) * kRowStride);
+        row[0] = row[1] = row[2] = row[3] = make_double2(0.0, 0.0);
+    }
+    // all 32 lanes, rows staged (the previous batch's reads ended with a __syncwarp)
+    __device__ __forceinline__ void accumulate_staged(const double *rows) {
+        const int lane = threadIdx.x & 31;
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) {
+            const double a = rows[(4 * ch + (lane & 3)) * kRowStride + (lane >> 2)];
+            dmma_m8n8k4(c0, c1, a, a);
+        }
+        __syncwarp();  // rows consumed before the next batch's are written
     }
 
     // all 32 lanes: stage the rows (zeros for lanes without a match) and accumulate their Gram matrix
@@ -358,6 +394,13 @@ __device__ __forceinline__ float lim_of(float sec, float cum) {
 // sqrt(d) * (1 + 1e-6) + cum, every step rounded UP: the moving side of the test (d = f32 distance + its band)
 __device__ __forceinline__ float reach_now(float d_ub, float cum_eps) {
     return __fadd_ru(__fmul_ru(__fsqrt_ru(d_ub), 1.000001f), cum_eps);
+}
+
+// the same test without the square root: sqrt(d)(1 + 1e-6) + cum_eps < lim  <=>  d (1 + 1e-6)^2 < (lim - cum_eps)^2 for a
+// positive right-hand side; left side rounded up, right side down.  A NaN or zero limit compares false.
+__device__ __forceinline__ bool within_limit(float d_ub, float cum_eps, float lim) {
+    const float m = __fsub_rd(lim, cum_eps);
+    return m > 0.0f && __fmul_ru(d_ub, 1.0000021f) < __fmul_rd(m, m);
 }
 
 // Part A's rare path: the nearest neighbour is known to be one of cand[0..3] (-1 = unused) but their f32
@@ -457,43 +500,65 @@ __global__ void __launch_bounds__(kPassTpb, VB_PASS_A_MINBLOCKS) k_pass_a(
     const float cum_eps = __fadd_ru(cum, pp.pos_err);
     unsigned char *my_hard = hard_ids + ((int64_t)blockIdx.x * kPassWarps + warp) * (32 * pp.pts);
     int nhard = 0;  // warp-uniform
+    const bool all_inside = st->all_inside != 0;
 #pragma unroll 1
     for (int k = 0; k < pp.pts; k++) {
         const int local = (warp * pp.pts + k) * 32 + lane;
         const bool valid = local < task.count;
-        double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        bool hard = false;
+        bool hard = false, staged = false;
         if (valid) {
             double vs[3];
             ctx.transform(src_xyz, pp.src_n, task.src_begin + local, vs);
             const int slot = task.corr_begin + local;
-            if (!inside_grid(G.p, vs[0], vs[1], vs[2])) {
+            if (!all_inside && !inside_grid(G.p, vs[0], vs[1], vs[2])) {
                 hot[slot].c0 = -1;  // farther than a cell outside the grid: no neighbour within the radius
             } else {
                 hard = true;
                 const HotRec h = hot[slot];
                 int match = -1;
+                double vt[3] = {0.0, 0.0, 0.0}, d2 = 0.0;
                 if (pp.use_cache && h.c0 >= 0) {
                     // |q - c0| (exact, rounded up) + move since the proof (upper bound) < distance to anything else
                     // then (lower bound); a NaN or zero limit (knows nothing) compares false
-                    const double d0x = l2_exact(vs[0], vs[1], vs[2], G.xyz + kPtStride * (int64_t)h.c0);
-                    if (reach_now(__double2float_ru(d0x), cum_eps) < h.lim1) match = h.c0;
-                    else match = settle_from_set(G, pp, vs[0], vs[1], vs[2], h.c0, slot, cum, cum_eps, hot, cold);
+                    const Rec3 t = ld_rec(G.xyz + kPtStride * (int64_t)h.c0);
+                    vt[0] = t.x; vt[1] = t.y; vt[2] = t.z;
+                    d2 = l2_exact(vs[0], vs[1], vs[2], t.x, t.y, t.z);
+                    if (within_limit(__double2float_ru(d2), cum_eps, h.lim1)) {
+                        match = h.c0;
+                    } else {
+                        match = settle_from_set(G, pp, vs[0], vs[1], vs[2], h.c0, slot, cum, cum_eps, hot, cold);
+                        if (match >= 0 && match != h.c0) {  // another member of the set won
+                            const Rec3 u = ld_rec(G.xyz + kPtStride * (int64_t)match);
+                            vt[0] = u.x; vt[1] = u.y; vt[2] = u.z;
+                            d2 = l2_exact(vs[0], vs[1], vs[2], u.x, u.y, u.z);
+                        }
+                    }
                 }
                 if (match >= 0) {
                     hard = false;
                     // still the nearest, but it may have left the radius: then there is no correspondence
                     // (and nothing to remember: c0 doubles as the correspondence list)
-                    if (!ctx.row_of(match, vs, pp.r2, x)) hot[slot].c0 = -1;
+                    if (d2 < pp.r2) {
+                        double nt[3] = {0.0, 0.0, 0.0};
+                        if (MODE == 1) {
+                            const Rec3 nn = ld_rec(G.nrm + kPtStride * (int64_t)match);
+                            nt[0] = nn.x; nt[1] = nn.y; nt[2] = nn.z;
+                        }
+                        ctx.stage_row(rows_sh[warp], vs, vt, nt, d2);
+                        staged = true;
+                    } else {
+                        hot[slot].c0 = -1;
+                    }
                 }
             }
         }
+        if (!staged) ctx.stage_zero_row(rows_sh[warp]);
         VB_STAT(12, hard);
         VB_STAT(13, valid && !hard);
         const unsigned hm = __ballot_sync(0xffffffffu, hard);
         if (hard) my_hard[nhard + __popc(hm & ((1u << lane) - 1u))] = (unsigned char)(k * 32 + lane);
         nhard += __popc(hm);
-        if (hm != 0xffffffffu) ctx.accumulate(rows_sh[warp], x);  // warp-uniform; nothing to add when every lane is hard
+        if (hm != 0xffffffffu) ctx.accumulate_staged(rows_sh[warp]);  // warp-uniform; nothing to add when every lane is hard
     }
     if (lane == 0) hard_cnt[blockIdx.x * kPassWarps + warp] = nhard;
     // one partial row per block: the warps' Gram matrices summed in warp order (rows_sh is free again)
@@ -778,7 +843,25 @@ __device__ void solve_from_totals(const double *tot, double npts, const ProbDesc
     }
     const float moved = __double2float_ru(update_move_bound(U, T, pd.ctr, pd.rad));
     mat4_mul(U, T, T);
+    // does the cloud's bounding sphere, under the new transform, lie inside the scene grid?  (centre T ctr, radius
+    // rad x the largest stretch of T's linear part, bounded by sqrt(max row sum of |R^T R|); margins for the rounding)
+    int all_inside = 1;
+    {
+        double s2 = 0.0;
+        for (int r = 0; r < 3; r++) {
+            double row = 0.0;
+            for (int k = 0; k < 3; k++) row += fabs(T[r] * T[k] + T[4 + r] * T[4 + k] + T[8 + r] * T[8 + k]);
+            s2 = fmax(s2, row);
+        }
+        const double rr = pd.rad * sqrt(s2) * (1.0 + 1e-9);
+        for (int a = 0; a < 3; a++) {
+            const double c = T[4 * a] * pd.ctr[0] + T[4 * a + 1] * pd.ctr[1] + T[4 * a + 2] * pd.ctr[2] + T[4 * a + 3];
+            const double m = 1e-9 * (fabs(c) + rr + 1.0);
+            if (!(c - rr - m >= sp.box_lo[a] && c + rr + m <= sp.box_hi[a])) all_inside = 0;  // (NaN: not inside)
+        }
+    }
     st->last_move = moved;
+    st->all_inside = all_inside;
     st->cum = __fadd_ru(cum, moved);
     for (int i = 0; i < 16; i++) st->T[i] = T[i];
     st->iters = pass_index + 1;
@@ -1478,6 +1561,13 @@ static int make_params(Batch *b, int estimator, const double *gravity, double ma
     memset(sp, 0, sizeof(*sp));
     sp->ndone = nullptr;
     sp->estimator = estimator;
+    for (int a = 0; a < 3; a++) {
+        // inside_grid accepts (x - lo) * inv_fine in [0, fdim): a box shrunk by a relative 1e-9 of its extent on each side
+        const GridParams &g = sc->grid.p;
+        const double ext = (double)g.fdim[a] / g.inv_fine;
+        sp->box_lo[a] = g.lo[a] + 1e-9 * (ext + fabs(g.lo[a]));
+        sp->box_hi[a] = g.lo[a] + ext - 1e-9 * (ext + fabs(g.lo[a]));
+    }
     sp->g[0] = 0.0; sp->g[1] = 1.0; sp->g[2] = 0.0;  // VISMA's gravity convention: +Y (src/annotation.cpp:43,84)
     if (estimator == VB200_EST_P2PLANE_GRAVITY && gravity) {
         double l = sqrt(gravity[0] * gravity[0] + gravity[1] * gravity[1] + gravity[2] * gravity[2]);
