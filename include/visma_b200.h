@@ -80,10 +80,13 @@ int vb200_knn1_device(vb200_scene_t *scene, const void *d_q_xyz, int64_t Q, doub
 /* The same operator by exhaustive search, without a scene handle: every (query, target) distance in the
  * reference's double arithmetic (flann::L2, O3D/3rdparty/flann/algorithms/dist.h:150-177), the target cloud
  * streamed through shared memory by the TMA engine.  Same outputs bit for bit as vb200_knn1 (same threshold
- * rule, ties to the lowest target index).  Meant for a handful of queries against a cloud nothing has indexed
- * yet (it streams 24 B per target point once per 8 queries and is FP64-bound beyond that) and as the
- * independent on-device check of the grid search.  Limits: Q <= 524 280 per call; the device variant needs a
- * 16-byte aligned target pointer and runs asynchronously on `cuda_stream` (a cudaStream_t, NULL = default). */
+ * rule, ties to the lowest target index).  Meant for queries against a cloud nothing has indexed yet and as the
+ * independent on-device check of the grid search.  Up to 15 queries it streams the cloud as it is (24 B per target
+ * point once per 8 queries, every distance in double: HBM-bound for 1-2 queries, FP64-bound beyond); from 16 queries
+ * it screens every pair in f32 on a packed copy of the cloud (3 FFMA + 1 compare per pair, a rigorous error band) and
+ * evaluates in double only the pairs that can matter.  Limits: Q <= 524 280 per call; the device variant needs a
+ * 16-byte aligned target pointer and is enqueued on `cuda_stream` (a cudaStream_t, NULL = default) — from 16
+ * queries it waits once for that stream (the bounding box of cloud and queries is read back to size the band). */
 int vb200_knn1_bruteforce(const double *tgt_xyz, int64_t n, const double *q_xyz, int64_t Q, double radius,
                           int device, int32_t *out_idx, double *out_d2);
 int vb200_knn1_bruteforce_device(const void *d_tgt_xyz, int64_t n, const void *d_q_xyz, int64_t Q, double radius,
