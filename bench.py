@@ -20,7 +20,7 @@ Total work is fixed as g grows: STRONG scaling.  value = K / (max over ranks of 
           sort, 30 iterations, D2H of the poses (+ the all-gather at N > 1), every call; iterations/s = 30 / call.
   roofline  the correspondence pass (k_pass_a + k_pass_b_wl): SURVEY §8d algorithmic bytes of the rank's share /
             its measured time (split-timing trajectory), with the search-bound and settled regimes beside the mean.
-  knn_sweep / render  the other two halves of BASELINE's metric (configs 5 and 4), N = 1 only.
+  knn_sweep / render / config2  the other halves of BASELINE's metric (configs 5, 4 and 2), N = 1 only.
   cpu_baseline  the unmodified reference (oracle/_ref) on a bounded sample of the same workload.
 """
 import argparse
@@ -307,6 +307,70 @@ def knn_sweep_leg(dev, flush, peak):
                     "bruteforce_fp32_frac_of_peak = 3 N Q / t / (128 lanes x 148 SMs x 1.965 GHz)."}
 
 
+def config2_leg(dev):
+    """BASELINE config 2 — "clutter1 scene (~2 M points) vs objects.json fragments, pose error vs alignment.json" — on
+    the generated stand-in in the reference's file layout (visma_b200/dataset.py; the recording itself is not available
+    offline): feh::AnnotationTool's per-object flow (src/annotation.cpp:103-141: voxel down-sample of the fragment,
+    2 x |scan| model samples, RegisterModelToScene with 24 yaw starts) through the library with host arrays, pose error
+    with MeasurePoseError's semantics (include/geometry.h:147-180), the CPU restatement of the same flow on one object."""
+    import tempfile
+    from visma_b200 import annotation, dataset, io3d, registration as reg
+    with tempfile.TemporaryDirectory() as tmp:
+        ds = dataset.write_clutter_dataset(tmp, n_scene=N_SCENE, n_objects=8)
+        cfg = io3d.load_json(ds["cfg_path"])
+        icp = cfg["ICP"]
+        floor, _ = io3d.read_ply(os.path.join(ds["fragment_dir"], "floor.ply"))
+        T0 = annotation.GravityAlignment(floor)
+        objs = []
+        for name in ds["entries"]:
+            scan, _ = io3d.read_ply(os.path.join(ds["fragment_dir"], name + ".ply"))
+            V, F = io3d.read_obj(os.path.join(ds["cad_dir"], name[:name.rfind("_")] + ".obj"))
+            objs.append((name, scan, V, F))
+        got, per_obj = {}, []
+        for rep in range(2):  # the second pass is the timed one (first: allocator pools, module load)
+            per_obj = []
+            for k, (name, scan, V, F) in enumerate(objs):
+                t0 = time.perf_counter()
+                n_scan = len(reg.VoxelDownSample(scan, icp["voxel_size"], dev.index).points_)
+                model = reg.SamplePointCloudFromMesh(V, F, 2 * n_scan, seed=k, device=dev.index)
+                Ttot, info = annotation.AnnotateObject(scan, model, T0, icp, dev.index)
+                per_obj.append(time.perf_counter() - t0)
+                got[name] = Ttot[:3, :4].copy()
+        keys = sorted(ds["T_gt"])
+        t_err, r_err = annotation.MeasurePoseError([got[k] for k in keys], [ds["T_gt"][k] for k in keys], 0.5)
+        out = {"dataset": "generated clutter1 stand-in: %d-point scene, 8 objects, fragments of %d-%d points"
+                          % (N_SCENE, min(len(o[1]) for o in objs), max(len(o[1]) for o in objs)),
+               "flow": "per object: VoxelDownSample(fragment, 0.01) + SamplePointCloudFromMesh(2 x |scan|) + "
+                       "RegisterModelToScene(24 yaw starts, threshold 0.02, point-to-point), host arrays in and out",
+               "ms_per_object": float(np.mean(per_obj) * 1e3), "objects_per_s": float(1.0 / np.mean(per_obj)),
+               "pose_error_vs_ground_truth": {"translation_m": t_err, "rotation_rad": r_err}}
+        # CPU: the same flow with the plain-C restatement's RegisterModelToScene on ONE object (bounded sample)
+        try:
+            from oracle import pyoracle
+            name, scan, V, F = objs[0]
+            n_scan = len(reg.VoxelDownSample(scan, icp["voxel_size"], dev.index).points_)
+            model = reg.SamplePointCloudFromMesh(V, F, 2 * n_scan, seed=0, device=dev.index)
+
+            def oracle_register(m, s2):
+                return pyoracle.register_model_to_scene(m, s2, level=icp["rotation_level"], threshold=icp["distance_threshold"],
+                                                        point_to_plane=False)
+            t0 = time.perf_counter()
+            To, _ = annotation.AnnotateObject(scan, model, T0, icp, register=oracle_register)
+            cpu_s = time.perf_counter() - t0
+            rot, tr = synth_pose_error(np.vstack([got[name], [0, 0, 0, 1]]), To)
+            out["cpu_baseline"] = {"s_per_object": cpu_s, "cores": 1, "kind": "port",
+                                   "sample": "object 0 of 8: the 24-start RegisterModelToScene of the CPU restatement"}
+            out["parity_vs_cpu_flow_object0"] = {"rot_rad": rot, "trans_m": tr, "within_1e-4_rad_1e-3_m": bool(rot < 1e-4 and tr < 1e-3)}
+        except Exception as ex:
+            out["cpu_baseline"] = "failed: %r" % (ex,)
+        return out
+
+
+def synth_pose_error(A, B):
+    from visma_b200 import synth
+    return synth.pose_error(A, B)
+
+
 def render_leg(dev, peak):
     """BASELINE config 4: 128 chair meshes @ 640x480, device-resident and through the C ABI with host buffers."""
     import torch
@@ -548,7 +612,8 @@ def run_ours(args):
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
         peak, _ = measured_peak()
-        for name, fn in (("knn_sweep", lambda: knn_sweep_leg(dev, flush, peak)), ("render", lambda: render_leg(dev, peak))):
+        for name, fn in (("knn_sweep", lambda: knn_sweep_leg(dev, flush, peak)), ("render", lambda: render_leg(dev, peak)),
+                         ("config2", lambda: config2_leg(dev))):
             try:
                 extra[name] = fn()
             except Exception as ex:  # a sub-bench must never lose the headline line
