@@ -2016,7 +2016,7 @@ static int estimate_from_host(const double *src_xyz, int64_t m, const double *tg
             nt[3 * i + c] = plane ? tgt_nrm[3 * bq + c] : 0.0;
         }
     }
-    vb::DevBuf<double> d_in;
+    vb::DevBuf<double> d_in((cudaStream_t) nullptr);  // stream-ordered on the default stream (estimate_on_device runs there)
     VB_CUDA(d_in.alloc((size_t)K * 9));
     VB_CUDA(cudaMemcpy(d_in.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
     return estimate_on_device(d_in.p, d_in.p + 3 * K, d_in.p + 6 * K, nullptr, K, estimator, gravity_axis, nullptr, out17);

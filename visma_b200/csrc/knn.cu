@@ -608,8 +608,8 @@ extern "C" int vb200_knn1(vb200_scene_t *scene, const double *q_xyz, int64_t Q, 
     VB_CUDA(cudaSetDevice(sc->device));
     if (!(radius > 0.0) || radius > sc->grid.p.cell * (1.0 + 1e-12)) return VB200_ERR_INVALID;
     if (Q == 0) return VB200_OK;
-    vb::DevBuf<double> d_q, d_d2;
-    vb::DevBuf<int> d_idx;
+    vb::DevBuf<double> d_q(sc->stream), d_d2(sc->stream);
+    vb::DevBuf<int> d_idx(sc->stream);
     VB_CUDA(d_q.alloc(3 * (size_t)Q));
     VB_CUDA(d_d2.alloc((size_t)Q));
     VB_CUDA(d_idx.alloc((size_t)Q));

@@ -94,9 +94,9 @@ extern "C" int vb200_sample_mesh(const float *V, int64_t nV, const int32_t *F, i
     cudaStream_t st;
     VB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
-    DevBuf<float> d_V;
-    DevBuf<int> d_F;
-    DevBuf<double> d_area, d_out, d_nrm;
+    DevBuf<float> d_V(st);
+    DevBuf<int> d_F(st);
+    DevBuf<double> d_area(st), d_out(st), d_nrm(st);
     VB_CUDA(d_V.alloc(3 * (size_t)nV));
     VB_CUDA(d_F.alloc(3 * (size_t)nF));
     VB_CUDA(d_area.alloc((size_t)nF));

@@ -144,7 +144,7 @@ int exclusive_scan_i32(const int *d_in, int *d_out, int64_t n, int *d_total, cud
 
 int device_bbox(const double *d_xyz, int64_t n, double lo[3], double hi[3], cudaStream_t stream) {
     const int nb = std::min(div_up(n, kBoxTpb), 4 * kNumSMsB200);
-    DevBuf<double> d_part;
+    DevBuf<double> d_part(stream);
     VB_CUDA(d_part.alloc(6 * (size_t)nb));
     k_bbox<<<nb, kBoxTpb, 0, stream>>>(d_xyz, n, d_part.p);
     VB_CUDA(cudaGetLastError());

@@ -132,7 +132,10 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     sc->n = n;
     sc->has_normals = h_nrm != nullptr;
     // raw upload (unsorted), freed after the gather
-    DevBuf<double> d_in_xyz, d_in_nrm;
+    // (every temporary and every array of the scene comes from the stream-ordered pool: with the pool's release
+    // threshold raised in select_device() a second scene reuses the first one's memory, where cudaMalloc / cudaFree
+    // cost milliseconds per call and synchronise the device)
+    DevBuf<double> d_in_xyz(st), d_in_nrm(st);
     VB_CUDA(d_in_xyz.alloc(3 * (size_t)n));
     VB_CUDA(cudaMemcpyAsync(d_in_xyz.p, h_xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
     if (h_nrm) {
@@ -182,9 +185,9 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     const int64_t ncoarse = (int64_t)g.cdim[0] * g.cdim[1] * g.cdim[2];
     sc->ncoarse = ncoarse;
 
-    DevBuf<int> d_ckey, d_ccount, d_cstart, d_cfcount, d_cbase, d_total;
-    DevBuf<unsigned char> d_fbit;
-    DevBuf<unsigned long long> d_skey, d_cmask;
+    DevBuf<int> d_ckey(st), d_ccount(st), d_cstart(st), d_cfcount(st), d_cbase(st), d_total(st);
+    DevBuf<unsigned char> d_fbit(st);
+    DevBuf<unsigned long long> d_skey(st), d_cmask(st);
     VB_CUDA(d_ckey.alloc((size_t)n));
     VB_CUDA(d_fbit.alloc((size_t)n));
     VB_CUDA(d_ccount.alloc((size_t)ncoarse + 1));
@@ -218,10 +221,10 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
         continue;  // the DevBufs of this attempt are released by their destructors
     }
 
-    DevBuf<CoarseCell> d_coarse;
-    DevBuf<int> d_fstart, d_orig;
-    DevBuf<float4> d_hi;
-    DevBuf<double> d_xyz, d_nrm;
+    DevBuf<CoarseCell> d_coarse(st);
+    DevBuf<int> d_fstart(st), d_orig(st);
+    DevBuf<float4> d_hi(st);
+    DevBuf<double> d_xyz(st), d_nrm(st);
     VB_CUDA(d_coarse.alloc((size_t)ncoarse));
     VB_CUDA(d_fstart.alloc((size_t)nfine + 1));
     VB_CUDA(d_hi.alloc((size_t)n));
@@ -286,12 +289,14 @@ int grid_order_points(const Scene *sc, const double *d_xyz, int64_t n, int *d_pe
 
 void scene_free(Scene *sc) {
     if (!sc) return;
-    cudaFree((void *)sc->grid.coarse);
-    cudaFree((void *)sc->grid.fstart);
-    cudaFree((void *)sc->grid.hi);
-    cudaFree((void *)sc->grid.xyz);
-    cudaFree((void *)sc->grid.nrm);
-    cudaFree((void *)sc->grid.orig);
+    // back to the pool, in stream order behind whatever the scene's streams still have queued
+    if (sc->stream2) cudaStreamSynchronize(sc->stream2);
+    const void *arrays[] = {sc->grid.coarse, sc->grid.fstart, sc->grid.hi, sc->grid.xyz, sc->grid.nrm, sc->grid.orig};
+    for (const void *a : arrays)
+        if (a) {
+            if (sc->stream) cudaFreeAsync(const_cast<void *>(a), sc->stream); else cudaFree(const_cast<void *>(a));
+        }
+    if (sc->stream) cudaStreamSynchronize(sc->stream);
     if (sc->stream2) cudaStreamDestroy(sc->stream2);
     if (sc->stream) cudaStreamDestroy(sc->stream);
     delete sc;

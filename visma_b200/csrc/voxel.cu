@@ -129,7 +129,7 @@ extern "C" int vb200_voxel_downsample(const double *xyz, const double *nrm, int6
     cudaStream_t st;
     VB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
-    DevBuf<double> d_xyz, d_nrm, d_out, d_out_n;
+    DevBuf<double> d_xyz(st), d_nrm(st), d_out(st), d_out_n(st);  // stream-ordered pool: no cudaMalloc / cudaFree per call
     VB_CUDA(d_xyz.alloc(3 * (size_t)n));
     VB_CUDA(cudaMemcpyAsync(d_xyz.p, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
     if (nrm) {
@@ -150,8 +150,8 @@ extern "C" int vb200_voxel_downsample(const double *xyz, const double *nrm, int6
     if (ext / voxel_size >= 2097152.0) return VB200_ERR_INVALID;       // 21 bits per axis in the packed key
     unsigned nslot = 1024;
     while ((int64_t)nslot < 2 * n) nslot <<= 1;
-    DevBuf<unsigned long long> d_table;
-    DevBuf<int> d_pslot, d_counts, d_start, d_first, d_rank, d_sidx, d_total;
+    DevBuf<unsigned long long> d_table(st);
+    DevBuf<int> d_pslot(st), d_counts(st), d_start(st), d_first(st), d_rank(st), d_sidx(st), d_total(st);
     VB_CUDA(d_table.alloc(nslot));
     VB_CUDA(d_pslot.alloc((size_t)n));
     VB_CUDA(d_sidx.alloc((size_t)n));
