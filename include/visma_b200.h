@@ -53,6 +53,9 @@ int vb200_version(void);
 const char *vb200_strerror(int status);
 const char *vb200_last_error(void); /* thread-local text of the last CUDA failure */
 int vb200_device_count(void);       /* 0 when no driver/GPU is present; never fails */
+/* Device memory the library has freed stays in CUDA's stream-ordered pool of that device (so that the next scene or
+ * batch does not pay cudaMalloc / cudaFree); this hands it back to the driver.  Live scenes and batches are untouched. */
+int vb200_release_cached_memory(int device);
 
 /* ---- scene: replaces KDTreeFlann::SetGeometry (O3D/src/Core/Geometry/KDTreeFlann.cpp:70-87,191-208),
  * which the reference re-runs inside EVERY RegistrationICP call (Registration.cpp:160-161).

@@ -200,6 +200,23 @@ def test_grid_search_equals_exhaustive_search_at_ten_million_points(vb, oracle):
     assert np.array_equal(np.where(hit, oi, -1), gi[pick]) and np.array_equal(np.where(hit, od, 0.0), gd[pick])
 
 
+def test_release_cached_memory_leaves_live_objects_alone(vb, oracle):
+    """vb200_release_cached_memory trims the stream-ordered pool the library allocates from: a live scene keeps
+    answering, and the next scene is built as before."""
+    rng = np.random.default_rng(4)
+    tgt = rng.uniform(0, 1, (20000, 3))
+    q = tgt[:500] + rng.normal(0, 0.004, (500, 3))
+    sc = vb.reg.Scene(tgt, 0.05)
+    a = sc.SearchHybrid1(q, 0.05)
+    vb.reg.Scene(tgt[:5000], 0.05).close()  # something freed into the pool
+    assert vb.lib.lib().vb200_release_cached_memory(0) == 0
+    b = sc.SearchHybrid1(q, 0.05)
+    c = vb.reg.Scene(tgt, 0.05).SearchHybrid1(q, 0.05)
+    oi, od = oracle.Index(tgt, 0.05).knn1(q, 0.05)
+    for gi, gd in (a, b, c):
+        assert (gi == oi).all() and (gd == od).all()
+
+
 def test_nan_points_are_never_neighbours(vb, oracle):
     """A NaN target or query point matches nothing (the reference's `dist < worst_dist` is false for NaN), in the
     grid search and in the exhaustive one, whatever the NaN's sign bit."""

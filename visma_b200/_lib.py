@@ -17,7 +17,7 @@ OPT_NN_CACHE, OPT_SPLIT_TIMING = 1, 2
 
 # every symbol include/visma_b200.h declares (tests/test_abi.py checks the two lists agree)
 SYMBOLS = [
-    "vb200_version", "vb200_strerror", "vb200_last_error", "vb200_device_count",
+    "vb200_version", "vb200_strerror", "vb200_last_error", "vb200_device_count", "vb200_release_cached_memory",
     "vb200_scene_create", "vb200_scene_destroy", "vb200_scene_size", "vb200_scene_stream",
     "vb200_scene_sync", "vb200_knn1", "vb200_knn1_device", "vb200_knn1_bruteforce", "vb200_knn1_bruteforce_device", "vb200_icp_run", "vb200_batch_create",
     "vb200_batch_destroy", "vb200_batch_set_problems", "vb200_batch_run", "vb200_batch_results",
@@ -62,6 +62,7 @@ def lib():
     L.vb200_strerror.argtypes = [C.c_int]
     L.vb200_last_error.restype = C.c_char_p
     L.vb200_device_count.restype = C.c_int
+    L.vb200_release_cached_memory.argtypes = [C.c_int]
     L.vb200_scene_create.argtypes = [dp, dp, C.c_int64, C.c_double, C.c_int, C.POINTER(vp)]
     L.vb200_scene_destroy.argtypes = [vp]
     L.vb200_scene_size.argtypes = [vp, i64p, i64p, i64p, dp]

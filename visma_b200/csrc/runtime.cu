@@ -49,6 +49,15 @@ extern "C" const char *vb200_strerror(int status) {
 
 extern "C" const char *vb200_last_error(void) { return vb::g_last_error; }
 
+extern "C" int vb200_release_cached_memory(int device) {
+    VB_TRY(vb::select_device(device));
+    cudaMemPool_t pool;
+    VB_CUDA(cudaDeviceSynchronize());
+    VB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    VB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return VB200_OK;
+}
+
 extern "C" int vb200_device_count(void) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess) {
