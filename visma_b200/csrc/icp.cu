@@ -37,11 +37,14 @@ namespace {
 #define VB_PASS_TPB 128
 #endif
 #ifndef VB_PASS_B_TPB
-#define VB_PASS_B_TPB 128  // part B's block: independent warps (no block-level barrier), 24 resident per SM -> 80 registers
+#define VB_PASS_B_TPB 128  // part B's block: independent warps (no block-level barrier)
 #endif
 constexpr int kPassBTpb = VB_PASS_B_TPB;
 constexpr int kPassBWarps = kPassBTpb / 32;
-constexpr int kPassBBlocksPerSM = 768 / kPassBTpb;
+#ifndef VB_PASS_B_WARPS_PER_SM
+#define VB_PASS_B_WARPS_PER_SM 32  // 64 registers: the search is latency-bound, 8 more warps per SM hide more than the extra spills cost
+#endif
+constexpr int kPassBBlocksPerSM = VB_PASS_B_WARPS_PER_SM * 32 / kPassBTpb;
 constexpr int kPassTpb = VB_PASS_TPB;
 constexpr int kPassWarps = kPassTpb / 32;  // every warp writes its own partial: no block-level barrier
 #ifndef VB_PASS_PTS
@@ -160,6 +163,10 @@ struct SolveParams {
 // ---- programmatic dependent launch: the three kernels of an iteration are chained with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's blocks are resident and past their
 // prologue when the previous one drains.  Nothing produced by the previous kernel is touched before pdl_wait().
+// One-sided fences at GPU scope.  __threadfence() is fence.sc: MEMBAR.SC + CCTL.IVALL, i.e. it also throws away every
+// line of the SM's L1 — the release side of a hand-off needs no invalidation at all, the acquire side only that.
+__device__ __forceinline__ void fence_release_gpu() { asm volatile("fence.release.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acquire.gpu;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 
@@ -708,12 +715,13 @@ __global__ void __launch_bounds__(kPassBTpb, kPassBBlocksPerSM) k_pass_b_wl(
         }
         double2 *brow = reinterpret_cast<double2 *>(pp.brows + ((int64_t)blk * (kPassWarps * pp.pts)) * kPart);
         brow[k * (kPart / 2) + lane] = ctx.lane_pair();
-        __threadfence();
+        fence_release_gpu();  // (not __threadfence(): that would also invalidate the SM's whole L1, once per batch)
+        __syncwarp();
         int prev = 0;
         if (lane == 0) prev = atomicAdd(pp.blk_done + blk, 1);
         prev = __shfl_sync(0xffffffffu, prev, 0);
         if (prev == nb - 1) {
-            __threadfence();
+            fence_acquire_gpu();
             if (lane == 0) pp.blk_done[blk] = 0;  // ready for the next pass
             double2 *arow = reinterpret_cast<double2 *>(partials + (int64_t)blk * kPart);
             double2 t = arow[lane];  // part A's row (the previous kernel's)
