@@ -1588,7 +1588,7 @@ static int make_params(Batch *b, int estimator, const double *gravity, double ma
 // Iterations [it_begin, it_end] of the loop (the whole loop is 0..max_iter): vb200_icp_run enqueues the first few
 // of one half of its clouds, uploads the other half meanwhile, then comes back for the rest.
 static int batch_run(Batch *b, int estimator, const double *gravity, double max_dist, double rel_fitness,
-                     double rel_rmse, int max_iter, int it_begin = 0, int it_end = 0x7fffffff) {
+                     double rel_rmse, int max_iter, int it_begin = 0, int it_end = 0x7fffffff, bool poll = true) {
     cudaStream_t st = b->stream;
     if (max_iter < 0) return VB200_ERR_INVALID;
     PassParams pp;
@@ -1605,7 +1605,7 @@ static int batch_run(Batch *b, int estimator, const double *gravity, double max_
     const bool can_stop = rel_fitness > 0.0 && rel_rmse > 0.0;
     if (can_stop) sp.ndone = b->d_ndone;
     for (int it = it_begin; it <= std::min(max_iter, it_end); it++) {
-        if (can_stop && it >= 4 && (it & 3) == 0) {
+        if (poll && can_stop && it >= 4 && (it & 3) == 0) {
             int ndone = 0;
             VB_CUDA(cudaMemcpyAsync(&ndone, b->d_ndone, sizeof(int), cudaMemcpyDeviceToHost, st));
             VB_CUDA(cudaStreamSynchronize(st));
@@ -1615,6 +1615,17 @@ static int batch_run(Batch *b, int estimator, const double *gravity, double max_
         VB_TRY(launch_solve(b, sp, it));
     }
     VB_CUDA(cudaGetLastError());
+    return VB200_OK;
+}
+
+// has every problem of the batch finished?  (waits for what has been enqueued on the batch's stream)
+static int batch_all_done(Batch *b, bool *done) {
+    *done = true;
+    if (b->P == 0 || !b->d_ndone) return VB200_OK;
+    int ndone = 0;
+    VB_CUDA(cudaMemcpyAsync(&ndone, b->d_ndone, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    VB_CUDA(cudaStreamSynchronize(b->stream));
+    *done = ndone >= b->P;
     return VB200_OK;
 }
 
@@ -1916,9 +1927,23 @@ extern "C" int vb200_icp_run(vb200_scene_t *scene, const double *src_xyz, const 
             rc = vb::batch_run(reinterpret_cast<Batch *>(half[h]), estimator, gravity_axis, max_dist, rel_fitness,
                                rel_rmse, max_iter, 0, nhalf == 2 ? warm : 0x7fffffff);
     }
-    for (int h = 0; h < nhalf && rc == VB200_OK && nhalf == 2; h++)
-        rc = vb::batch_run(reinterpret_cast<Batch *>(half[h]), estimator, gravity_axis, max_dist, rel_fitness, rel_rmse,
-                           max_iter, warm + 1);
+    if (nhalf == 2 && rel_fitness > 0.0 && rel_rmse > 0.0) {
+        // a live convergence test: four iterations of BOTH halves are enqueued, then the host looks at both finished-
+        // problems counters — the halves' tails overlap on the device instead of the second waiting for the first's polls
+        bool fin[2] = {false, false};
+        for (int it0 = warm + 1; it0 <= max_iter && rc == VB200_OK && !(fin[0] && fin[1]); it0 += 4) {
+            for (int h = 0; h < 2 && rc == VB200_OK; h++)
+                if (!fin[h])
+                    rc = vb::batch_run(reinterpret_cast<Batch *>(half[h]), estimator, gravity_axis, max_dist, rel_fitness,
+                                       rel_rmse, max_iter, it0, it0 + 3, false);
+            for (int h = 0; h < 2 && rc == VB200_OK; h++)
+                if (!fin[h]) rc = vb::batch_all_done(reinterpret_cast<Batch *>(half[h]), &fin[h]);
+        }
+    } else {
+        for (int h = 0; h < nhalf && rc == VB200_OK && nhalf == 2; h++)
+            rc = vb::batch_run(reinterpret_cast<Batch *>(half[h]), estimator, gravity_axis, max_dist, rel_fitness, rel_rmse,
+                               max_iter, warm + 1);
+    }
     for (int h = 0; h < nhalf && rc == VB200_OK; h++) {
         const int p0 = first[h], np = first[h + 1] - first[h];
         rc = vb200_batch_results(half[h], out_T ? out_T + 16 * (size_t)p0 : nullptr, out_fitness ? out_fitness + p0 : nullptr,
