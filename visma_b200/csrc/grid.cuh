@@ -274,43 +274,6 @@ static __device__ __noinline__ int nn_exact_rescan(const GridDev &G, const Query
     return bs;
 }
 
-__device__ __forceinline__ int nn_search(const GridDev &G, const QueryCtx &c, double qx, double qy, double qz,
-                                         double r2, float r2_ub, double *d2_out) {
-    const GridParams &g = G.p;
-    Screen r;
-    r.best = r2_ub; r.second = 3.0e38f; r.bs = -1;
-    // 1. home fine cell first: gives a tight bound that prunes almost everything else
-    {
-        const int hcx = c.gx >> 2, hcy = c.gy >> 2, hcz = c.gz >> 2;
-        const CoarseCell cc = G.coarse[((int64_t)hcz * g.cdim[1] + hcy) * g.cdim[0] + hcx];
-        const int hbit = (c.gx & 3) + 4 * (c.gy & 3) + 16 * (c.gz & 3);
-        if ((cc.mask >> hbit) & 1ull) {
-            int rank = __popcll(cc.mask & ((1ull << hbit) - 1ull));
-            int s0 = __ldg(G.fstart + cc.base + rank), s1 = __ldg(G.fstart + cc.base + rank + 1);
-            scan_run(G.hi, s0, s1, c, r);
-        }
-    }
-    // 2. every other fine cell within reach of the current bound.  The runner-up matters too (ambiguity
-    //    test), so the reach covers second-best candidates inside the band of the best.
-    float reach2 = fminf(r.best + 2.0f * band(g, r.best), r2_ub);
-    auto visit = [&](int s0, int s1, float gap2) {
-        if (gap2 > fminf(r.best + 2.0f * band(g, r.best), r2_ub)) return;
-        scan_run(G.hi, s0, s1, c, r);
-    };
-    walk_cells(G, c, reach2, true, visit);
-    if (r.bs < 0) { *d2_out = 0.0; return -1; }
-    // 3. decide in double
-    float bb = band(g, r.best);
-    if (r.second - r.best > bb + band(g, r.second)) {
-        // unique f32 winner, and (second starts at r2_ub) it is also clear of the threshold band
-        double d = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)r.bs);
-        if (d < r2) { *d2_out = d; return r.bs; }
-        *d2_out = 0.0;
-        return -1;
-    }
-    return nn_exact_rescan(G, c, qx, qy, qz, r2, fminf(r.best + 2.0f * bb, r2_ub), d2_out);
-}
-
 // ---- warp-cooperative search -----------------------------------------------------------------------------
 // A per-lane cell walk diverges badly when the 32 lanes of a warp visit different cells (first version,
 // measured: 4.5 of 32 lanes active per issued instruction).  Instead the warp repeatedly picks a leader lane,
@@ -496,33 +459,6 @@ __device__ __forceinline__ Screen coop_screen(const GridDev &G, unsigned pending
         if (member) r = rr;
     }
     return r;
-}
-
-// The decision in double from a completed f32 screening (per lane): the winner's exact d2 against the
-// reference's threshold, or the double re-walk when the f32 result is ambiguous.
-__device__ __forceinline__ int nn_decide(const GridDev &G, const Screen &r, const QueryCtx &c, double qx, double qy,
-                                         double qz, double r2, float r2_ub, double *d2_out, bool *unique = nullptr) {
-    const GridParams &g = G.p;
-    *d2_out = 0.0;
-    if (unique) *unique = false;
-    if (r.bs < 0) return -1;
-    const float bb = band(g, r.best);
-    if (r.second - r.best > bb + band(g, r.second)) {
-        if (unique) *unique = true;  // r.bs is the true nearest: every other point is farther even in double
-        const double d = l2_exact(qx, qy, qz, G.xyz + kPtStride * (int64_t)r.bs);
-        if (d < r2) { *d2_out = d; return r.bs; }
-        return -1;
-    }
-    return nn_exact_rescan(G, c, qx, qy, qz, r2, fminf(r.best + 2.0f * bb, r2_ub), d2_out);
-}
-
-// All 32 lanes of the warp must call this together.  `valid` = this lane has a query inside the grid.
-__device__ __forceinline__ int nn_search_warp(const GridDev &G, bool valid, const QueryCtx &c, double qx, double qy,
-                                              double qz, double r2, float r2_ub, double *d2_out) {
-    const Screen r = coop_screen(G, __ballot_sync(0xffffffffu, valid), c, r2_ub);
-    *d2_out = 0.0;
-    if (!valid) return -1;
-    return nn_decide(G, r, c, qx, qy, qz, r2, r2_ub, d2_out);
 }
 
 // ---- lane-private search ----------------------------------------------------------------------------------
