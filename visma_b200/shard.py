@@ -87,15 +87,27 @@ def register_global_sharded(scene, source_shard, init, max_dist, estimation, cri
     batch.set_problems(np.asarray(init, np.float64).reshape(1, 16))
     totals = torch.zeros(32, dtype=torch.float64, device=dev)
     batch.set_totals_buffer(totals.data_ptr())
+    # NCCL reduces the device buffer in place; under gloo (two ranks sharing one GPU in the tests) the 256 bytes go
+    # through the host — either way every rank ends up with bit-identical totals
+    via_host = world > 1 and dist.get_backend(group) != "nccl"
+
+    def all_reduce(t):
+        if via_host:
+            h = t.cpu()
+            dist.all_reduce(h, group=group)
+            t.copy_(h)
+        else:
+            dist.all_reduce(t, group=group)
+
     n_local = torch.tensor([batch.sizes[0]], dtype=torch.int64, device=dev)
     if world > 1:
-        dist.all_reduce(n_local, group=group)
+        all_reduce(n_local)
     n_global = [int(n_local.item())]
     for it in range(criteria.max_iteration_ + 1):
         batch.pass_(estimation, max_dist)
         scene.sync()                      # totals written on the library's stream
         if world > 1:
-            dist.all_reduce(totals, group=group)
+            all_reduce(totals)
             torch.cuda.synchronize(dev)
         batch.solve(estimation, max_dist, criteria, it, n_global)
     res = batch.results()[0]
