@@ -1,6 +1,7 @@
 // tests/cpp/sharded_check.cpp — visma_b200::RegistrationICPSharded (visma_b200/host/sharded_b200.h) on the GPUs of
 // this box: one host thread per GPU (ncclCommInitAll), each with its own scene replica, against the single-GPU
-// RegistrationICPBatch of all the objects.  TEST INFRASTRUCTURE; built by `make -C oracle sharded` where
+// RegistrationICPBatch of all the objects, and visma_b200::RegistrationICPGlobalSharded (one cloud cut into slices, a
+// 256-byte ncclAllReduce per iteration) against the single-GPU alignment of the whole cloud.  TEST INFRASTRUCTURE; built by `make -C oracle sharded` where
 // /root/reference exists (Open3D headers), run by tests/test_gpu_dropin.py.
 //
 //   usage: sharded_check <input.bin> [world]     world defaults to min(device count, 2)
@@ -75,6 +76,33 @@ int main(int argc, char **argv) {
                                                              nullptr, &ncorr[r]);
         });
     for (auto &t : th) t.join();
+    // the other split: ONE cloud (object 0) cut into `world` slices, one 256-byte all-reduce per iteration, against the
+    // single-GPU alignment of the whole cloud
+    open3d::RegistrationResult whole(inits[0]);
+    {
+        visma_b200::Scene scene(target, max_d, 0);
+        whole = visma_b200::RegistrationICPBatch({&src[0]}, scene, max_d, {inits[0]}, p2l)[0];
+    }
+    std::vector<open3d::RegistrationResult> glob(world, open3d::RegistrationResult(inits[0]));
+    th.clear();
+    for (int r = 0; r < world; r++)
+        th.emplace_back([&, r]() {
+            cudaSetDevice(devs[r]);
+            visma_b200::Scene scene(target, max_d, devs[r]);
+            const size_t m = src[0].points_.size(), a = r * m / world, e = (r + 1) * m / world;
+            open3d::PointCloud slice;
+            slice.points_.assign(src[0].points_.begin() + a, src[0].points_.begin() + e);
+            slice.normals_.assign(src[0].normals_.begin() + a, src[0].normals_.begin() + e);
+            glob[r] = visma_b200::RegistrationICPGlobalSharded(slice, scene, max_d, inits[0], p2l,
+                                                               open3d::ICPConvergenceCriteria(), comms[r]);
+        });
+    for (auto &t : th) t.join();
+    double g_dT = 0, g_dfit = 0, g_ranks = 0;
+    for (int r = 0; r < world; r++) {
+        g_dT = std::max(g_dT, max_abs_diff(glob[r].transformation_, whole.transformation_));
+        g_dfit = std::max(g_dfit, std::abs(glob[r].fitness_ - whole.fitness_) + std::abs(glob[r].inlier_rmse_ - whole.inlier_rmse_));
+        g_ranks = std::max(g_ranks, max_abs_diff(glob[r].transformation_, glob[0].transformation_));
+    }
     for (auto &c : comms) ncclCommDestroy(c);
     double worst = 0, worst_fit = 0;
     int ncorr_bad = 0, own_sets = 0;
@@ -87,7 +115,8 @@ int main(int argc, char **argv) {
             if (b % world == r) own_sets += per_rank[r][b].correspondence_set_ == single[b].correspondence_set_;
         }
     printf("\nJSON:{\"world\": %d, \"objects\": %d, \"max_dT\": %.3e, \"max_dfit\": %.3e, \"ncorr_mismatches\": %d, "
-           "\"own_correspondence_sets_equal\": %d, \"fitness0\": %.6f}\n",
-           world, B, worst, worst_fit, ncorr_bad, own_sets, single[0].fitness_);
+           "\"own_correspondence_sets_equal\": %d, \"fitness0\": %.6f, \"global_max_dT\": %.3e, \"global_max_dfit\": %.3e, "
+           "\"global_rank_spread\": %.3e, \"global_fitness\": %.6f}\n",
+           world, B, worst, worst_fit, ncorr_bad, own_sets, single[0].fitness_, g_dT, g_dfit, g_ranks, whole.fitness_);
     return 0;
 }

@@ -72,3 +72,7 @@ def test_cpp_sharded_host_path_equals_single_gpu(tmp_path):
     assert r["objects"] == 5 and r["world"] >= 1
     assert r["max_dT"] == 0 and r["max_dfit"] == 0 and r["ncorr_mismatches"] == 0
     assert r["own_correspondence_sets_equal"] == 5 and r["fitness0"] > 0.9
+    # RegistrationICPGlobalSharded: one cloud cut into slices, per-iteration ncclAllReduce of the totals — the same
+    # transform on every rank, equal to the single-GPU alignment up to the summation order of the totals
+    assert r["global_rank_spread"] == 0 and r["global_fitness"] > 0.9
+    assert r["global_max_dT"] < 1e-9 and r["global_max_dfit"] < 1e-9

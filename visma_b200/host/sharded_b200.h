@@ -3,6 +3,8 @@
 // objects {b : b mod world == r} with one batched launch sequence, and ONE ncclAllGather of the pose table (20
 // doubles per object: the 4x4 row-major, fitness, inlier rmse, correspondence count, iterations) leaves all the
 // results on every rank.  There is no per-iteration exchange: the objects are independent problems.
+// RegistrationICPGlobalSharded is the other split — ONE cloud sharded over the ranks, one 256-byte ncclAllReduce per
+// iteration (ICPRefinement's global transform).
 //
 // Header-only on top of registration_b200.h; NCCL and the CUDA runtime are dependencies of the INCLUDING target
 // only (libvisma_b200.so itself links neither NCCL nor MPI).
@@ -81,6 +83,71 @@ inline std::vector<open3d::RegistrationResult> RegistrationICPSharded(
         }
     }
     for (size_t k = 0; k < mine.size(); k++) out[mine[k]].correspondence_set_ = std::move(my_res[k].correspondence_set_);
+    return out;
+}
+
+/// ONE source cloud sharded over the ranks of `comm` — feh::ICPRefinement's single global transform
+/// (src/evaluation.cpp:244-274) at multi-GPU scale.  Every rank passes ITS slice of the cloud and its own scene
+/// replica; an iteration is vb200_batch_pass (correspondence pass over the slice, 32 totals left on the device) ->
+/// ncclAllReduce of those 256 bytes on the library's stream -> vb200_batch_solve (fitness / rmse / convergence test /
+/// estimator update from the combined totals).  Every rank sees bit-identical totals and applies the identical
+/// update, so the transforms stay consistent without a broadcast; the result (without a correspondence set: it
+/// would be the slice's) is the same on every rank.  Errors follow RegistrationICP: RegistrationResult(init).
+inline open3d::RegistrationResult RegistrationICPGlobalSharded(
+        const open3d::PointCloud &source_slice, const Scene &target, double max_correspondence_distance,
+        const Eigen::Matrix4d &init, const open3d::TransformationEstimation &estimation,
+        const open3d::ICPConvergenceCriteria &criteria, ncclComm_t comm) {
+    open3d::RegistrationResult out(init);
+    if (max_correspondence_distance <= 0.0) {
+        open3d::PrintError("Error: Invalid max_correspondence_distance.\n");
+        return out;
+    }
+    const int kind = EstimatorKind(estimation);
+    // (every rank must take the same branch: a slice may be empty, so the cloud-level property is the caller's to keep)
+    if (kind != VB200_EST_P2P && !source_slice.points_.empty() && !source_slice.HasNormals()) {
+        open3d::PrintError("Error: TransformationEstimationPointToPlane requires pre-computed normal vectors.\n");
+        return out;
+    }
+    cudaStream_t st = (cudaStream_t)vb200_scene_stream(target.handle());
+    const int64_t off[2] = {0, (int64_t)source_slice.points_.size()};
+    const double dummy[3] = {0.0, 0.0, 0.0};
+    const double *xyz = source_slice.points_.empty() ? dummy : Raw(source_slice.points_);
+    vb200_batch_t *batch = nullptr;
+    double T0[16], T[16], fit = 0.0, rmse = 0.0;
+    ToRowMajor(init, T0);
+    double *d_totals = nullptr;       // 32 totals, then the slice's point count as a double (exact below 2^53)
+    bool ok = vb200_batch_create(target.handle(), xyz, kind != VB200_EST_P2P ? xyz : nullptr, off, 1, &batch) == VB200_OK &&
+              vb200_batch_set_problems(batch, nullptr, T0, 1) == VB200_OK &&
+              cudaMalloc((void **)&d_totals, 33 * sizeof(double)) == cudaSuccess &&
+              cudaMemsetAsync(d_totals, 0, 33 * sizeof(double), st) == cudaSuccess &&
+              vb200_batch_set_totals_buffer(batch, d_totals) == VB200_OK;
+    int64_t n_global = 0;
+    if (ok) {
+        double n_local = (double)off[1], n_sum = 0.0;
+        ok = cudaMemcpyAsync(d_totals + 32, &n_local, sizeof(double), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+             ncclAllReduce(d_totals + 32, d_totals + 32, 1, ncclDouble, ncclSum, comm, st) == ncclSuccess &&
+             cudaMemcpyAsync(&n_sum, d_totals + 32, sizeof(double), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+             cudaStreamSynchronize(st) == cudaSuccess;
+        n_global = (int64_t)n_sum;
+    }
+    for (int it = 0; ok && it <= criteria.max_iteration_; it++) {
+        ok = vb200_batch_pass(batch, kind, max_correspondence_distance) == VB200_OK &&
+             ncclAllReduce(d_totals, d_totals, 32, ncclDouble, ncclSum, comm, st) == ncclSuccess &&
+             vb200_batch_solve(batch, kind, GravityAxis(estimation), max_correspondence_distance,
+                               criteria.relative_fitness_, criteria.relative_rmse_, criteria.max_iteration_, it,
+                               &n_global) == VB200_OK;
+    }
+    int32_t nc = 0, iters = 0;
+    ok = ok && vb200_batch_results(batch, T, &fit, &rmse, &nc, &iters) == VB200_OK;
+    if (batch) vb200_batch_destroy(batch);
+    cudaFree(d_totals);
+    if (!ok) {
+        open3d::PrintError("visma_b200::RegistrationICPGlobalSharded: %s\n", vb200_last_error());
+        return out;
+    }
+    out.transformation_ = FromRowMajor(T);
+    out.fitness_ = fit;
+    out.inlier_rmse_ = rmse;
     return out;
 }
 
