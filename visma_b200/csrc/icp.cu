@@ -1349,7 +1349,7 @@ static int batch_upload(Batch *b, const double *src_xyz, const int64_t *off, int
     VB_CUDA(d_counts.alloc(nb));
     VB_CUDA(d_start.alloc(nb));
     VB_CUDA(d_bounds.alloc(7 * (size_t)ncloud));
-    VB_CUDA(cudaMemcpyAsync(d_in.p, src_xyz + 3 * off[0], sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+    VB_CUDA(h2d_async(d_in.p, src_xyz + 3 * off[0], sizeof(double) * 3 * (size_t)n, st));
     VB_CUDA(cudaMemsetAsync(d_counts.p, 0, sizeof(int) * nb, st));
     const double inv_half = 2.0 / sc->grid.p.cell;
     k_src_keys<<<div_up(n, 256), 256, 0, st>>>(d_in.p, n, b->d_cloud_off, ncloud, inv_half, d_key.p, d_counts.p);

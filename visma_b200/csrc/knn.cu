@@ -645,7 +645,7 @@ extern "C" int vb200_knn1_bruteforce(const double *tgt_xyz, int64_t n, const dou
     VB_CUDA(d_q.alloc(3 * (size_t)Q));
     VB_CUDA(d_d2.alloc((size_t)Q));
     VB_CUDA(d_idx.alloc((size_t)Q));
-    if (n) VB_CUDA(cudaMemcpyAsync(d_t.p, tgt_xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (n) VB_CUDA(vb::h2d_async(d_t.p, tgt_xyz, sizeof(double) * 3 * (size_t)n, st));
     VB_CUDA(cudaMemcpyAsync(d_q.p, q_xyz, sizeof(double) * 3 * (size_t)Q, cudaMemcpyHostToDevice, st));
     VB_TRY(vb::bf_launch(d_t.p, n, d_q.p, Q, radius, d_idx.p, d_d2.p, st));
     VB_CUDA(cudaMemcpyAsync(out_idx, d_idx.p, sizeof(int) * (size_t)Q, cudaMemcpyDeviceToHost, st));

@@ -137,10 +137,10 @@ int scene_build(Scene *sc, const double *h_xyz, const double *h_nrm, int64_t n, 
     // cost milliseconds per call and synchronise the device)
     DevBuf<double> d_in_xyz(st), d_in_nrm(st);
     VB_CUDA(d_in_xyz.alloc(3 * (size_t)n));
-    VB_CUDA(cudaMemcpyAsync(d_in_xyz.p, h_xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+    VB_CUDA(h2d_async(d_in_xyz.p, h_xyz, sizeof(double) * 3 * (size_t)n, st));
     if (h_nrm) {
         VB_CUDA(d_in_nrm.alloc(3 * (size_t)n));
-        VB_CUDA(cudaMemcpyAsync(d_in_nrm.p, h_nrm, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+        VB_CUDA(h2d_async(d_in_nrm.p, h_nrm, sizeof(double) * 3 * (size_t)n, st));
     }
     // bounding box
     double lo[3], hi[3];

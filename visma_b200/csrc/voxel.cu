@@ -131,10 +131,10 @@ extern "C" int vb200_voxel_downsample(const double *xyz, const double *nrm, int6
     struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
     DevBuf<double> d_xyz(st), d_nrm(st), d_out(st), d_out_n(st);  // stream-ordered pool: no cudaMalloc / cudaFree per call
     VB_CUDA(d_xyz.alloc(3 * (size_t)n));
-    VB_CUDA(cudaMemcpyAsync(d_xyz.p, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+    VB_CUDA(h2d_async(d_xyz.p, xyz, sizeof(double) * 3 * (size_t)n, st));
     if (nrm) {
         VB_CUDA(d_nrm.alloc(3 * (size_t)n));
-        VB_CUDA(cudaMemcpyAsync(d_nrm.p, nrm, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+        VB_CUDA(h2d_async(d_nrm.p, nrm, sizeof(double) * 3 * (size_t)n, st));
     }
     double lo[3], hi[3];
     VB_TRY(device_bbox(d_xyz.p, n, lo, hi, st));
