@@ -232,3 +232,33 @@ def test_nan_points_are_never_neighbours(vb, oracle):
     assert (gi == oi).all() and (gd == od).all()
     assert (bi == oi).all() and (bd == od).all()
     assert not np.isin(gi, [5, 700, 1500]).any() and gi[-1] == -1 and gi[-2] == -1
+
+
+def test_pageable_upload_is_staged_and_exact(vb):
+    """Uploads of 16 MB or more from PAGEABLE host memory go through the library's staged copy (host threads ->
+    pinned slots -> copy engine, runtime.cu h2d_async): the scene built from a pageable array — odd size, source
+    pointer off the 16-byte grid — must answer exactly like the scene built from a pinned copy of the same points
+    (which takes the direct path), and like the exhaustive search."""
+    import torch
+    n = 1_000_003                                    # 24 MB of coordinates + 24 MB of normals, not a multiple of any chunk
+    d = vb.synth.make_room_scene(n, 1, 1000, seed=11)
+    raw = np.empty(3 * n + 1, np.float64)
+    xyz = raw[1:].reshape(n, 3)                      # 8 bytes off the allocation's alignment
+    xyz[:] = d["scene_xyz"]
+    nrm = np.ascontiguousarray(d["scene_nrm"])
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    q = xyz[::211] + 0.004
+    a = vb.reg.Scene(vb.reg.PointCloud(xyz, nrm), 0.075)
+    b = vb.reg.Scene(vb.reg.PointCloud(pin(xyz), pin(nrm)), 0.075)
+    ia, da = a.SearchHybrid1(q, 0.075)
+    ib, db = b.SearchHybrid1(q, 0.075)
+    assert (ia == ib).all() and (da == db).all() and (ia >= 0).sum() > len(q) // 2
+    # the exhaustive search uploads the same pageable array itself (staged as well)
+    ic, dc = vb.reg.SearchHybrid1BruteForce(xyz, q[:64], 0.075)
+    assert (ic == ia[:64]).all() and (dc == da[:64]).all()
+    # and the normals went up intact: a point-to-plane alignment of a slice of the scene onto itself is the identity
+    src = vb.reg.PointCloud(xyz[5000:25000].copy(), nrm[5000:25000].copy())
+    for s in (a, b):
+        r = vb.reg.RegistrationICP(src, s, 0.02, np.eye(4), vb.reg.TransformationEstimationPointToPlane())
+        assert r.fitness_ == 1.0 and np.abs(r.transformation_ - np.eye(4)).max() < 1e-12
+    a.close(); b.close()
