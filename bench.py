@@ -700,7 +700,7 @@ def run_ours(args):
                          "traffic": profiled_traffic(), "peak_source": how, "algorithmic_bytes": b_alg,
                          "search_bound": {"pass_ms": p_search, "achieved": b_alg / (p_search * 1e-3) / 1e9,
                                           "frac": b_alg / (p_search * 1e-3) / 1e9 / peak,
-                                          "note": "iterations 0-5: every point is searched (instruction-issue bound)"},
+                                          "note": "iterations 0-5: every point is searched (bound by the latency of the search's dependent loads and its per-lane run lists, not by HBM)"},
                          "settled": {"pass_ms": p_settled, "achieved": b_alg / (p_settled * 1e-3) / 1e9,
                                      "frac": b_alg / (p_settled * 1e-3) / 1e9 / peak,
                                      "note": "iterations 20-29 (cached-neighbour regime: part A streams, part B "
